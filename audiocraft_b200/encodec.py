@@ -1,0 +1,342 @@
+"""EnCodec on B200: host-side mirror of ``audiocraft.models.encodec`` over the C-ABI kernels.
+
+``CompressionModel`` keeps the reference's abstract surface (audiocraft/models/encodec.py:28-122);
+``EncodecModel`` keeps ``encode / decode / decode_latent / preprocess / postprocess`` and the properties
+(audiocraft/models/encodec.py:125-259) but is built from a reference-layout ``state_dict`` + hyper-parameters
+instead of nn.Modules: weight-norm is folded once at load on the GPU, conv weights are re-packed tap-major,
+and every layer is one fused kernel (padding, ELU, bias, residual, trim inside).
+
+PyTorch here is plumbing only (device memory, streams).  There is no CPU path: without the CUDA library
+or a GPU, construction raises.
+"""
+import math
+import typing as tp
+from abc import ABC, abstractmethod
+
+import torch
+
+from . import _lib
+from .synth import ENCODEC_CONFIGS, encodec_hop, encodec_layers
+
+
+class CompressionModel(ABC):
+    """Same abstract API as audiocraft.models.encodec.CompressionModel (encodec.py:28-122)."""
+
+    @abstractmethod
+    def forward(self, x: torch.Tensor): ...
+
+    @abstractmethod
+    def encode(self, x: torch.Tensor) -> tp.Tuple[torch.Tensor, tp.Optional[torch.Tensor]]: ...
+
+    @abstractmethod
+    def decode(self, codes: torch.Tensor, scale: tp.Optional[torch.Tensor] = None): ...
+
+    @abstractmethod
+    def decode_latent(self, codes: torch.Tensor): ...
+
+    @property
+    @abstractmethod
+    def channels(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def frame_rate(self) -> float: ...
+
+    @property
+    @abstractmethod
+    def sample_rate(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def cardinality(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def num_codebooks(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def total_codebooks(self) -> int: ...
+
+    @abstractmethod
+    def set_num_codebooks(self, n: int): ...
+
+    def eval(self):
+        return self
+
+    def __call__(self, x):
+        return self.forward(x)
+
+    @staticmethod
+    def get_pretrained(name: str, device='cuda') -> 'CompressionModel':
+        """The reference downloads checkpoints from the HF hub (encodec.py:87-122).  There is no network here:
+        `name` may be a local checkpoint file in the reference's export format
+        ({'best_state', 'xp.cfg'} -- audiocraft/utils/export.py:20-79) or one of the synthetic architectures."""
+        from .loaders import load_compression_model
+        return load_compression_model(name, device=device)
+
+
+# ----------------------------------------------------------------------------- host-side padding rules
+
+def extra_padding(length: int, k_eff: int, stride: int, padding_total: int) -> int:
+    """get_extra_padding_for_conv1d, audiocraft/modules/conv.py:47-53."""
+    n_frames = (length - k_eff + padding_total) / stride + 1
+    return (math.ceil(n_frames) - 1) * stride + (k_eff - padding_total) - length
+
+
+def conv_geometry(length: int, kernel: int, stride: int, dilation: int, causal: bool, reflect: bool):
+    """(pad_left, t_virtual, t_out) of StreamableConv1d.forward for an input of `length` steps
+    (audiocraft/modules/conv.py:185-200 + the short-input rule of pad1d :71-88)."""
+    k_eff = (kernel - 1) * dilation + 1
+    total = k_eff - stride
+    extra = extra_padding(length, k_eff, stride, total)
+    if causal:
+        left, right = total, extra
+    else:
+        right = total // 2
+        left = total - right
+        right += extra
+    t_virtual = length
+    if reflect and length <= max(left, right):
+        t_virtual = length + (max(left, right) - length + 1)
+    t_out = (length + left + right - k_eff) // stride + 1
+    return left, t_virtual, t_out
+
+
+def convtr_geometry(length: int, kernel: int, stride: int, causal: bool, trim_right_ratio: float):
+    """(trim_left, t_out) of StreamableConvTranspose1d.forward (audiocraft/modules/conv.py:221-243)."""
+    total = kernel - stride
+    if causal:
+        right = math.ceil(total * trim_right_ratio)
+        left = total - right
+    else:
+        right = total // 2
+        left = total - right
+    t_full = (length - 1) * stride + kernel
+    return left, t_full - left - right
+
+
+class EncodecModel(CompressionModel):
+    """EnCodec (SEANet + RVQ) on B200 behind the reference's ``EncodecModel`` API."""
+
+    def __init__(self, state_dict: tp.Dict[str, torch.Tensor], cfg: dict, device='cuda'):
+        self.device = _lib.require_cuda(device)
+        self._lib = _lib.lib()
+        self.cfg = dict(cfg)
+        self._channels = cfg['channels']
+        self._sample_rate = cfg['sample_rate']
+        self._frame_rate = cfg['sample_rate'] / encodec_hop(cfg)
+        self.causal = cfg['causal']
+        self.renormalize = cfg.get('renormalize', False)
+        if self.causal:
+            assert not self.renormalize, 'Causal model does not support renormalize'  # encodec.py:163-166
+        self.max_n_q = cfg['n_q']
+        self.n_q = cfg['n_q']
+        self.bins = cfg['bins']
+        self.dimension = cfg['dimension']
+        self.reflect = 1 if cfg['pad_mode'] == 'reflect' else 0
+        assert cfg['pad_mode'] in ('reflect', 'constant', 'zeros'), cfg['pad_mode']
+        self.launches = 0
+        plan = encodec_layers(cfg)
+        with torch.cuda.device(self.device):
+            self.enc = [self._prepare(layer, state_dict) for layer in plan['encoder']]
+            self.dec = [self._prepare(layer, state_dict) for layer in plan['decoder']]
+            cb = torch.stack([state_dict[f'quantizer.vq.layers.{k}._codebook.embed'].float()
+                              for k in range(self.max_n_q)]).to(self.device).contiguous()
+            self.codebooks = cb                                        # [n_q][bins][D]
+            self.cb_sqnorm = cb.pow(2).sum(-1).contiguous()            # |e_j|^2, core_vq.py:169
+            torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------ weight preparation (once)
+    def _fold(self, sd, prefix):
+        if prefix + 'weight_g' in sd:
+            v = sd[prefix + 'weight_v'].to(self.device, torch.float32).contiguous()
+            g = sd[prefix + 'weight_g'].to(self.device, torch.float32).contiguous()
+            w = torch.empty_like(v)
+            _lib.check(self._lib.acb_weight_norm_fold(_lib.ptr(v), _lib.ptr(g), _lib.ptr(w), v.shape[0],
+                                                      v[0].numel(), _lib.stream()), 'weight_norm_fold')
+            return w
+        return sd[prefix + 'weight'].to(self.device, torch.float32).contiguous()
+
+    def _prepare(self, layer: dict, sd) -> dict:
+        out = dict(layer)
+        p = layer['prefix']
+        if layer['kind'] == 'conv':
+            w = self._fold(sd, p)                                       # [Cout][Cin][K]
+            out['w'] = w.permute(1, 2, 0).reshape(-1, w.shape[0]).contiguous()   # [Cin*K][Cout]
+            out['b'] = sd[p + 'bias'].to(self.device, torch.float32).contiguous()
+        elif layer['kind'] == 'convtr':
+            w = self._fold(sd, p)                                       # [Cin][Cout][K]
+            out['w'] = w.permute(0, 2, 1).contiguous()                  # [Cin][K][Cout]
+            out['b'] = sd[p + 'bias'].to(self.device, torch.float32).contiguous()
+        else:
+            out['w_ih'], out['w_hh'], out['bias'] = [], [], []
+            for n in range(layer['layers']):
+                w_ih = sd[f'{p}weight_ih_l{n}'].to(self.device, torch.float32)
+                out['w_ih'].append(w_ih.t().contiguous())              # 1x1 conv packing [H][4H]
+                out['w_hh'].append(sd[f'{p}weight_hh_l{n}'].to(self.device, torch.float32).contiguous())
+                out['bias'].append((sd[f'{p}bias_ih_l{n}'].float() + sd[f'{p}bias_hh_l{n}'].float())
+                                   .to(self.device).contiguous())
+        return out
+
+    # ------------------------------------------------------------------ layer launches
+    def _conv(self, x, L, w=None, b=None, res=None, k=None, stride=None, dilation=None, elu=None, cout=None):
+        B, cin, T = x.shape
+        k = L['k'] if k is None else k
+        stride = L['stride'] if stride is None else stride
+        dilation = L['dilation'] if dilation is None else dilation
+        cout = L['cout'] if cout is None else cout
+        left, t_virt, t_out = conv_geometry(T, k, stride, dilation, self.causal, bool(self.reflect))
+        y = torch.empty((B, cout, t_out), device=x.device, dtype=torch.float32)
+        _lib.check(self._lib.acb_conv1d(_lib.ptr(x), _lib.ptr(L['w'] if w is None else w),
+                                        _lib.ptr(L['b'] if b is None else b), _lib.ptr(res), _lib.ptr(y),
+                                        B, cin, cout, T, t_virt, t_out, k, stride, dilation, left, self.reflect,
+                                        int(L['elu'] if elu is None else elu), _lib.stream()), 'conv1d')
+        self.launches += 1
+        return y
+
+    def _convtr(self, x, L):
+        B, cin, T = x.shape
+        trim_left, t_out = convtr_geometry(T, L['k'], L['stride'], self.causal, self.cfg['trim_right_ratio'])
+        y = torch.empty((B, L['cout'], t_out), device=x.device, dtype=torch.float32)
+        _lib.check(self._lib.acb_convtr1d(_lib.ptr(x), _lib.ptr(L['w']), _lib.ptr(L['b']), _lib.ptr(y), B, cin,
+                                          L['cout'], T, t_out, L['k'], L['stride'], trim_left, int(L['elu']),
+                                          _lib.stream()), 'convtr1d')
+        self.launches += 1
+        return y
+
+    def _lstm(self, x, L):
+        """y = LSTM(x) + x over frames (audiocraft/modules/lstm.py:19-25): per layer one 1x1 conv for the input
+        half of the gates, then the persistent recurrent kernel."""
+        B, H, T = x.shape
+        ws = torch.empty(int(self._lib.acb_lstm_state_bytes(B, H)) // 4, device=x.device, dtype=torch.float32)
+        inp = x
+        n_layers = len(L['w_hh'])
+        for n in range(n_layers):
+            gx = torch.empty((B, 4 * H, T), device=x.device, dtype=torch.float32)
+            _lib.check(self._lib.acb_conv1d(_lib.ptr(inp), _lib.ptr(L['w_ih'][n]), _lib.ptr(L['bias'][n]), None,
+                                            _lib.ptr(gx), B, H, 4 * H, T, T, T, 1, 1, 1, 0, 0, 0, _lib.stream()),
+                       'lstm input conv')
+            y = torch.empty((B, H, T), device=x.device, dtype=torch.float32)
+            skip = x if n == n_layers - 1 else None
+            _lib.check(self._lib.acb_lstm_recurrent(_lib.ptr(gx), _lib.ptr(L['w_hh'][n]), _lib.ptr(skip), _lib.ptr(y),
+                                                    _lib.ptr(ws), B, H, T, _lib.stream()), 'lstm_recurrent')
+            self.launches += 2
+            inp = y
+        return inp
+
+    def _run(self, x, layers):
+        skip = None
+        for L in layers:
+            if L['kind'] == 'conv':
+                if L['res'] == 'in':
+                    skip = x
+                res = skip if L['res'] == 'out' else None
+                x = self._conv(x, L, res=res)
+            elif L['kind'] == 'convtr':
+                x = self._convtr(x, L)
+            else:
+                x = self._lstm(x, L)
+        return x
+
+    # ------------------------------------------------------------------ reference API
+    @property
+    def total_codebooks(self):
+        return self.max_n_q
+
+    @property
+    def num_codebooks(self):
+        return self.n_q
+
+    def set_num_codebooks(self, n: int):
+        assert n > 0 and n <= self.max_n_q   # vq.py:113-115
+        self.n_q = n
+
+    @property
+    def cardinality(self):
+        return self.bins
+
+    @property
+    def channels(self):
+        return self._channels
+
+    @property
+    def frame_rate(self):
+        return self._frame_rate
+
+    @property
+    def sample_rate(self):
+        return self._sample_rate
+
+    def preprocess(self, x):
+        """encodec.py:186-196."""
+        if self.renormalize:
+            mono = x.mean(dim=1, keepdim=True)
+            volume = mono.pow(2).mean(dim=2, keepdim=True).sqrt()
+            scale = 1e-8 + volume
+            return x / scale, scale.view(-1, 1)
+        return x, None
+
+    def postprocess(self, x, scale=None):
+        if scale is not None:
+            assert self.renormalize
+            x = x * scale.view(-1, 1, 1)
+        return x
+
+    def _in(self, x):
+        assert x.dim() == 3
+        assert x.shape[1] == self._channels, f"expected {self._channels} channels, got {x.shape[1]}"
+        return x.to(self.device, torch.float32).contiguous()
+
+    def encode_latent(self, x):
+        """SEANetEncoder.forward (audiocraft/modules/seanet.py:152-153) on pre-processed input."""
+        with torch.cuda.device(self.device):
+            return self._run(self._in(x), self.enc)
+
+    def quantize(self, emb):
+        """ResidualVectorQuantizer.encode (vq.py:87-96): latent [B,D,T] -> codes [B,n_q,T] int64."""
+        B, D, T = emb.shape
+        codes = torch.empty((B, self.n_q, T), device=emb.device, dtype=torch.int64)
+        _lib.check(self._lib.acb_rvq_encode(_lib.ptr(emb.contiguous()), _lib.ptr(self.codebooks),
+                                            _lib.ptr(self.cb_sqnorm), _lib.ptr(codes), B, D, T, self.n_q, self.bins,
+                                            _lib.stream()), 'rvq_encode')
+        self.launches += 1
+        return codes
+
+    def encode(self, x):
+        """encodec.py:223-238."""
+        with torch.cuda.device(self.device):
+            x, scale = self.preprocess(self._in(x))
+            emb = self._run(x.contiguous(), self.enc)
+            return self.quantize(emb), scale
+
+    def decode_latent(self, codes):
+        """encodec.py:257-259 -> vq.py:98-103."""
+        assert codes.dim() == 3
+        with torch.cuda.device(self.device):
+            codes = codes.to(self.device, torch.int64).contiguous()
+            B, K, T = codes.shape
+            assert K <= self.max_n_q
+            out = torch.empty((B, self.dimension, T), device=self.device, dtype=torch.float32)
+            _lib.check(self._lib.acb_rvq_decode(_lib.ptr(codes), _lib.ptr(self.codebooks), _lib.ptr(out), B,
+                                                self.dimension, T, K, self.bins, _lib.stream()), 'rvq_decode')
+            self.launches += 1
+            return out
+
+    def decode(self, codes, scale=None):
+        """encodec.py:240-255; like the reference the output keeps the decoder's extra padding."""
+        with torch.cuda.device(self.device):
+            out = self._run(self.decode_latent(codes), self.dec)
+            return self.postprocess(out, scale)
+
+    def forward(self, x):
+        """encodec.py:206-221 (inference part): returns the reconstruction trimmed to the input length and codes."""
+        length = x.shape[-1]
+        codes, scale = self.encode(x)
+        out = self.decode(codes, scale)
+        assert out.shape[-1] >= length, (out.shape[-1], length)
+        return out[..., :length], codes
+
+    @staticmethod
+    def from_config_name(name: str, state_dict, device='cuda') -> 'EncodecModel':
+        return EncodecModel(state_dict, ENCODEC_CONFIGS[name], device)

@@ -1,0 +1,319 @@
+"""bench.py -- MusicGen-medium text-conditioned 30 s generation, batch 8 per GPU (BASELINE.json configs[2]), the
+configuration the headline metric `audio-sec/sec` is quoted on; it fits one B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--duration 30] [--batch 8]
+  torchrun --nproc-per-node N bench.py --gpus N ...
+
+One "step" = one full pass of the hot path over one batch: LMModel.generate (T+3 decode steps, CFG rows = 2B) followed
+by EnCodec decode of the tokens to audio.  `value` = audio seconds produced by all ranks / max-over-ranks device time,
+inputs (condition tensors) resident in HBM.  `e2e` = the same through the public MusicGen.generate(descriptions) call
+with host inputs (text-encoder states pinned on the host, copied inside the timed region) and the waveform read back.
+Weights are seeded random (no checkpoints offline), inputs synthetic.
+
+`--impl reference` times the reference's own CPU implementation of the path: /root/reference does not exist on the GPU
+box, so it runs the oracle port (oracle/lm_oracle.py + oracle/encodec_oracle.py, fp32, all host threads) on a bounded
+sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MusicGen-medium audio-sec/sec @30s gen"
+UNIT = "audio-s/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm_gbs=j['hbm_gbs'], source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (recipe in B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '200',
+                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def dist_setup(n):
+    if n <= 1:
+        return 0, 1
+    import torch.distributed as dist
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    local = int(os.environ.get('LOCAL_RANK', rank))
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    dist.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
+    return rank, world
+
+
+def algorithmic_bytes(lm, rows, S):
+    """per decode step W_step + rows*t*kv_tok (read) + rows*kv_tok (write), fp16."""
+    kv_tok = 2 * lm.dim * 2 * lm.num_layers
+    w = lm.weight_bytes_per_step
+    total = 0
+    for t in range(1, S):  # step at position t-1 attends t keys
+        total += w + rows * t * kv_tok + rows * kv_tok
+    return w, kv_tok, total
+
+
+def run_b200(args):
+    rank, world = dist_setup(args.gpus)
+    assert torch.cuda.is_available(), "bench.py (impl b200) needs a CUDA device; there is no CPU fallback"
+    dev = torch.device('cuda', torch.cuda.current_device())
+    from audiocraft_b200 import _lib
+    from audiocraft_b200.loaders import load_musicgen
+    import ctypes as C
+    torch.manual_seed(1234 + rank)
+    B, dur = args.batch, args.duration
+    mg = load_musicgen(f'synthetic/{args.scale}', device=dev, seed=0)
+    mg.set_generation_params(duration=dur, use_sampling=True, top_k=250, temperature=1.0, cfg_coef=3.0)
+    lm, cm = mg.lm, mg.compression_model
+    T = int(dur * mg.frame_rate)
+    S = T + 3 + 1
+    descriptions = [f"synthetic prompt number {i} for rank {rank} with a few more words" for i in range(B)]
+    # device-resident inputs for `value`: the fused condition tensor [2B, T_text, d]
+    from audiocraft_b200.conditioners import ConditioningAttributes
+    attrs = [ConditioningAttributes(text={'description': d}) for d in descriptions]
+    cross = lm._prepare_conditions(attrs, False, None).contiguous()
+    # host inputs for `e2e`: the text-encoder hidden states, pinned
+    enc = lm.condition_provider.conditioners['description'].encoder
+    hid, msk = enc(descriptions + [""] * B)
+    hid_pinned, msk_pinned = hid.pin_memory(), msk.pin_memory()
+    h2d_bytes = hid.numel() * 4 + msk.numel() * 8
+
+    def step_device():
+        tokens = lm.generate(None, [], num_samples=B, max_gen_len=T, cross_attention_src=cross, **mg.generation_params)
+        return mg.generate_audio(tokens)
+
+    def step_e2e():
+        # what MusicGen.generate(descriptions) does, with the encoder states coming from pinned host memory
+        h = hid_pinned.to(dev, non_blocking=True)
+        m_ = msk_pinned.to(dev, non_blocking=True)
+        m_[B:] = 0
+        cond = lm.condition_provider.conditioners['description']({'hidden': h, 'attention_mask': m_})[0]
+        tokens = lm.generate(None, [], num_samples=B, max_gen_len=T, cross_attention_src=cond, **mg.generation_params)
+        wav = mg.generate_audio(tokens)
+        return wav.to('cpu', non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def timed(fn, n):
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, out
+
+    for _ in range(args.warmup):
+        l0 = cm.launches
+        wav = step_device()
+        dec_launches = cm.launches - l0   # EnCodec decode kernels per generate
+    torch.cuda.synchronize()
+    with ClockSampler(torch.cuda.current_device()) as clk:
+        ms, wav = timed(step_device, args.steps)
+    clocks = clk.summary()
+    audio_s = B * dur * world * args.steps
+    value = audio_s / (ms / 1e3)
+    ms_e2e, wav_host = timed(step_e2e, max(1, min(args.steps, 2)))
+    e2e_value = B * dur * world * max(1, min(args.steps, 2)) / (ms_e2e / 1e3)
+    d2h_bytes = wav_host.numel() * 4
+
+    # ---- dominant kernel (lm_gemm_kernel) timed in isolation with CUDA events on the launching stream.
+    # One pass = every weight matrix of one decode step (W_step bytes >> 126 MB L2, so passes do not hit in L2).
+    rows = 2 * B
+    w_step, kv_tok, total_bytes = algorithmic_bytes(lm, rows, S)
+    nl = C.c_int(0)
+    reps = 20
+    for _ in range(3):
+        _lib.check(lm._lib.acb_lm_debug_gemms(lm._handle, _lib.stream(), C.byref(nl)))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        _lib.check(lm._lib.acb_lm_debug_gemms(lm._handle, _lib.stream(), C.byref(nl)))
+    e1.record()
+    torch.cuda.synchronize()
+    gemm_ms = e0.elapsed_time(e1) / reps
+    pk = peaks()
+    achieved = w_step / (gemm_ms / 1e3) / 1e9
+    step_ms = ms / args.steps / (S - 1)  # includes the EnCodec decode, amortised
+    roofline = dict(bound='hbm', kernel='lm_gemm_kernel', achieved=round(achieved, 1), peak=pk['hbm_gbs'], unit='GB/s',
+                    frac=round(achieved / pk['hbm_gbs'], 4), traffic=None, peak_source=pk['source'],
+                    launches_per_pass=nl.value, bytes_per_pass=w_step, ms_per_pass=round(gemm_ms, 4),
+                    whole_generate=dict(algorithmic_bytes=total_bytes, achieved=round(total_bytes / (ms / args.steps / 1e3) / 1e9, 1),
+                                        frac=round(total_bytes / (ms / args.steps / 1e3) / 1e9 / pk['hbm_gbs'], 4),
+                                        ms_per_decode_step=round(step_ms, 4)))
+
+    # ---- secondary metric: EnCodec 32 kHz encode+decode MSamples/s (BASELINE configs[3] per-GPU slice, 32 x 10 s)
+    secondary = None
+    if not args.no_encodec:
+        xb = torch.randn(32, 1, 320000, device=dev) * 0.1
+        for _ in range(2):
+            c_, _s = cm.encode(xb)
+            cm.decode(c_)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            c_, _s = cm.encode(xb)
+            y_ = cm.decode(c_)
+        e1.record()
+        torch.cuda.synchronize()
+        enc_ms = e0.elapsed_time(e1) / 3
+        secondary = dict(metric='EnCodec 32kHz encode+decode MSamples/sec', value=round(xb.numel() / (enc_ms / 1e3) / 1e6, 2),
+                         unit='MSamples/s', config='32 x 10 s mono per GPU, fp32', ms=round(enc_ms, 2))
+
+    cpu_baseline = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+        cpu_baseline = cpu_reference(args, sample_steps=args.cpu_steps)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f16', data='synthetic',
+                    config=dict(workload=f'MusicGen-{args.scale} text-conditioned {dur:g}s generation, batch={B} per GPU '
+                                         f'(CFG rows={2 * B}), top_k=250, EnCodec-32k decode included',
+                                global_batch=B * world, seq_len=T, parallelism=f'dp{world} (batch split, no collective)',
+                                l2='inputs larger than L2: every decode step streams %.2f GB of weights' % (w_step / 1e9)),
+                    clocks=clocks,
+                    e2e=dict(value=round(e2e_value, 2), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes),
+                    gpu_launches=(lm.launches_per_step * (S - 1) + dec_launches) * args.steps,
+                    roofline=roofline, cpu_baseline=cpu_baseline, secondary=secondary)
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def cpu_reference(args, sample_steps):
+    """The oracle port of the reference's CPU path on the host cores: the first `sample_steps` decode steps of the same
+    workload (rows = 2B, fp32, all threads) + EnCodec-32k decode of 1 s of tokens, scaled to audio-s/s."""
+    from oracle import lm_oracle as LO
+    from audiocraft_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.lm_config({'small': 'musicgen_small', 'medium': 'musicgen_medium', 'large': 'musicgen_large'}[args.scale])
+    gdev = 'cuda' if torch.cuda.is_available() else 'cpu'
+    sd = synth.synth_lm_state_dict(cfg, 0, device=gdev, dtype=torch.float16 if gdev == 'cuda' else torch.float32)
+    sd = {k: v.float().cpu() for k, v in sd.items()}
+    B = args.batch
+    o = LO.LMOracle(sd, cfg)
+    del sd
+    cross = torch.randn(2 * B, 16, cfg['dim']) * 0.1
+    cross[B:] = 0
+    seq = torch.full((B, cfg['n_q'], 1), cfg['card'], dtype=torch.long)
+    o.reset()
+    g = torch.Generator().manual_seed(0)
+    o.next_token(seq, cross, True, 1.0, 250, 0.0, 3.0, g, None)  # warm-up step (also fills 1 KV entry)
+    t0 = time.perf_counter()
+    for _ in range(sample_steps):
+        seq = o.next_token(seq, cross, True, 1.0, 250, 0.0, 3.0, g, None)
+    dt = time.perf_counter() - t0
+    per_step = dt / sample_steps
+    frame_rate = 50.0
+    value = B / frame_rate / per_step  # audio seconds per wall second (EnCodec decode excluded: <1% of the CPU time)
+    return dict(value=round(value, 4), unit=UNIT, cores=cores, kind='port',
+                sample=f'{sample_steps} decode steps of the batch={B} (rows={2 * B}) {args.scale} generation at KV length<= '
+                       f'{sample_steps + 1}, fp32 oracle port, {per_step * 1e3:.0f} ms/step; short-context steps are the '
+                       f'cheapest ones, so this favours the CPU')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    cb = cpu_reference(args, sample_steps=max(2, args.cpu_steps))
+    line = dict(metric=METRIC, value=cb['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=round((time.perf_counter() - t0) * 1e3, 1), higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload=f'MusicGen-{args.scale} text-conditioned {args.duration:g}s generation, batch={args.batch} '
+                                     f'(CFG rows={2 * args.batch}); bounded sample, see cpu_baseline.sample'),
+                cpu_baseline=cb, e2e=dict(value=cb['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--scale', default='medium', choices=['small', 'medium', 'large'])
+    ap.add_argument('--duration', type=float, default=30.0)
+    ap.add_argument('--batch', type=int, default=8)
+    ap.add_argument('--cpu-steps', type=int, default=6)
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-encodec', action='store_true')
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

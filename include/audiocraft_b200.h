@@ -1,0 +1,204 @@
+/*
+ * audiocraft_b200 -- C-ABI of the B200 (sm_100a) hot-path library.
+ *
+ * The reference (facebookresearch/audiocraft) is 100% Python and has no FFI layer; its boundary for
+ * this path is the Python class API (CompressionModel / LMModel / MusicGen).  This header is the
+ * boundary a native replacement exports underneath those classes; each entry point cites the
+ * reference function it replaces (paths relative to the reference repo root).  INTEGRATION.md shows
+ * the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative acb_status otherwise; acb_last_error() gives
+ *     a human readable message for the calling thread.  No C++ exception crosses the ABI.
+ *   - all pointers are DEVICE pointers unless named host_*; the caller (PyTorch) owns every buffer,
+ *     including KV caches and workspaces.  The library allocates nothing after acb_lm_create().
+ *   - all work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t passed as void*),
+ *     nothing synchronises the device, so every call is CUDA-graph capturable unless noted.
+ *   - handles are not thread-safe; one handle per device.
+ *   - tensors are dense row-major; "BCT" means [batch][channel][time] float32.
+ */
+#ifndef AUDIOCRAFT_B200_H
+#define AUDIOCRAFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ACB_OK = 0,
+    ACB_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+    ACB_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    ACB_ERR_UNSUPPORTED = -3, /* valid in the reference, not built here (say which in last_error) */
+} acb_status;
+
+int acb_version(void);
+const char* acb_last_error(void);
+/* Device properties the host side sizes its launches with. */
+int acb_device_sm_count(int device);
+
+/* ---------------------------------------------------------------- EnCodec: SEANet convolutions ---- */
+
+/* w[g][i] = g[g] * v[g][i] / ||v[g]||_2   (one warp-shuffle reduction per group).
+ * Replaces the weight_norm forward pre-hook that audiocraft/modules/conv.py:21-30 installs and that
+ * recomputes the weight on EVERY forward; here it is folded once at load.  groups = dim 0 of the
+ * parameter (Cout for Conv1d, Cin for ConvTranspose1d), inner = product of the other dims. */
+int acb_weight_norm_fold(const float* v, const float* g, float* w, int groups, int inner, void* stream);
+
+/* StreamableConv1d.forward, audiocraft/modules/conv.py:185-201, with the padding folded into index
+ * math (no F.pad copy) and the surrounding elementwise ops fused:
+ *   y[b,co,t] = bias[co] + sum_{ci,k} w[ci*K+k][co] * act(xpad[b,ci,t*stride + k*dilation - pad_left])
+ *               (+ residual[b,co,t])
+ *   act = ELU(alpha=1) if elu_in else identity  (the nn.ELU that precedes the conv, seanet.py:45,131,143)
+ *   xpad = reflect (reflect=1; with the short-input rule of conv.py:71-88: virtual length t_virtual >= t_in,
+ *          zeros past t_in) or zero padding (reflect=0) of x; pad_left / t_out come from the host, which
+ *          mirrors get_extra_padding_for_conv1d (conv.py:47-53).
+ *   residual: the true-skip input of SEANetResnetBlock (seanet.py:59-60), or NULL.
+ * w_packed is [Cin*K][Cout] (tap-major, Cout contiguous), folded fp32 weights. */
+int acb_conv1d(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
+               int batch, int c_in, int c_out, int t_in, int t_virtual, int t_out, int kernel, int stride,
+               int dilation, int pad_left, int reflect, int elu_in, void* stream);
+
+/* StreamableConvTranspose1d.forward, audiocraft/modules/conv.py:221-243: transposed conv (kernel = 2*stride)
+ * followed by the fixed trim, computed directly in trimmed coordinates:
+ *   y[b,co,o] = bias[co] + sum_ci ( act(x[b,ci,ti]) * w[ci][p][co] + act(x[b,ci,ti-1]) * w[ci][p+stride][co] ),
+ *   u = o + trim_left, ti = u / stride, p = u % stride, x outside [0,t_in) = 0.
+ * w_packed is [Cin][K][Cout].  Supported strides: 2,3,4,5,8 with kernel == 2*stride. */
+int acb_convtr1d(const float* x, const float* w_packed, const float* bias, float* y,
+                 int batch, int c_in, int c_out, int t_in, int t_out, int kernel, int stride, int trim_left,
+                 int elu_in, void* stream);
+
+/* Recurrent half of StreamableLSTM.forward, audiocraft/modules/lstm.py:19-25 (nn.LSTM, gate order i,f,g,o,
+ * zero initial state).  The input half (W_ih x_t + b_ih + b_hh for every t) is a 1x1 acb_conv1d producing
+ * gates_x [B][4H][T]; this call runs the T dependent steps in ONE persistent cooperative kernel that keeps
+ * its slice of W_hh resident in shared memory:
+ *   y[b,:,t] = h_t (+ skip[b,:,t] if skip != NULL)       [B][H][T]
+ * state_ws: >= (2*B*H + 64) floats of scratch (h double buffer + grid-barrier counter), zeroed by the call.
+ * NOT graph-capturable (cooperative launch). */
+int acb_lstm_recurrent(const float* gates_x, const float* w_hh, const float* skip, float* y, float* state_ws,
+                       int batch, int hidden, int t_len, void* stream);
+/* bytes of state_ws needed by acb_lstm_recurrent */
+int64_t acb_lstm_state_bytes(int batch, int hidden);
+
+/* ---------------------------------------------------------------- EnCodec: residual VQ ------------- */
+
+/* ResidualVectorQuantizer.encode, audiocraft/quantization/vq.py:87-96 -> core_vq.py:386-396 -> :164-172,
+ * fused per codebook: score_j = -(|r|^2 - 2 r.e_j + |e_j|^2) in fp32, first-max argmax, r -= e_idx.
+ * The [frames x bins] distance matrix never goes to HBM.
+ *   latent [B][D][T] fp32, codebooks [n_q][bins][D] fp32, cb_sqnorm [n_q][bins] fp32 (sum_d e^2),
+ *   codes [B][n_q][T] int64.  D must be a multiple of 4 and <= 512. */
+int acb_rvq_encode(const float* latent, const float* codebooks, const float* cb_sqnorm, int64_t* codes,
+                   int batch, int dim, int t_len, int n_q, int bins, void* stream);
+
+/* ResidualVectorQuantizer.decode, vq.py:98-103 -> core_vq.py:398-404: latent[b,:,t] = sum_k E_k[codes[b,k,t]]. */
+int acb_rvq_decode(const int64_t* codes, const float* codebooks, float* latent,
+                   int batch, int dim, int t_len, int n_q, int bins, void* stream);
+
+/* ---------------------------------------------------------------- MusicGen: LM decode -------------- */
+
+typedef struct {
+    int dim;          /* d_model */
+    int num_heads;    /* head_dim must be 64 */
+    int num_layers;
+    int ffn_dim;      /* hidden_scale * dim */
+    int n_q;          /* codebooks (4) */
+    int card;         /* cardinality (2048); special token id == card */
+    int cross_attention; /* 1: layers have cross attention to the text condition */
+    int max_rows;     /* rows = B (no CFG) or 2B (CFG: [cond rows; null rows]) the buffers are sized for */
+    int max_seq;      /* S = T + max_delay + 1, KV cache length */
+    int max_text;     /* cross-attention source length the cross KV cache is sized for */
+    float pos_scale;  /* positional_scale */
+} acb_lm_config;
+
+/* fp16 matrices in the reference's own [out_features][in_features] layout, stacked over layers. */
+typedef struct {
+    const void* emb;      /* [n_q][card+1][d] fp16       LMModel.emb, lm.py:160-163 */
+    const float* inv_freq;/* [d/2] fp32: max_period^(i/(d/2-1)), create_sin_embedding transformer.py:70-89 */
+    const void* w_qkv;    /* [L][3d][d]   self_attn.in_proj_weight (packed p,h,hd; transformer.py:373) */
+    const void* w_o;      /* [L][d][d]    self_attn.out_proj.weight */
+    const void* w_cq;     /* [L][d][d]    cross_attention.in_proj_weight[:d] */
+    const void* w_ckv;    /* [L][2d][d]   cross_attention.in_proj_weight[d:] */
+    const void* w_co;     /* [L][d][d]    cross_attention.out_proj.weight */
+    const void* w_ff1;    /* [L][ffn][d]  linear1.weight */
+    const void* w_ff2;    /* [L][d][ffn]  linear2.weight */
+    const float* ln;      /* [L][6][d] fp32: norm1.w, norm1.b, norm_cross.w, norm_cross.b, norm2.w, norm2.b */
+    const float* out_norm;/* [2][d] fp32 */
+    const void* heads;    /* [n_q*card][d] fp16  LMModel.linears, lm.py:172 */
+} acb_lm_weights;
+
+/* Caller-owned state; sizes in elements.  rows_pad = max_rows rounded up to 8. */
+typedef struct {
+    float* x;          /* [rows_pad][d]            residual stream */
+    void* h16;         /* [rows_pad][d] fp16       LayerNorm output / GEMM input */
+    void* a16;         /* [rows_pad][d] fp16       attention output */
+    void* f16;         /* [rows_pad][ffn] fp16     gelu(linear1) */
+    float* q32;        /* [rows_pad][d]            self-attention queries */
+    float* part;       /* [ACB_LM_MAX_SPLIT][rows_pad][d]  split-K partial sums */
+    float* logits;     /* [rows_pad][n_q*card] */
+    void* k_cache;     /* [L][max_rows][H][max_seq][64] fp16 */
+    void* v_cache;     /* same */
+    void* ck_cache;    /* [L][max_rows][H][max_text][64] fp16  cross-attention keys (computed once per generate) */
+    void* cv_cache;    /* same, values */
+    void* cross16;     /* [max_rows*max_text rounded up to 64][d] fp16  staging of the condition tensor */
+    int64_t* seq;      /* [B][n_q][max_seq]  delay-pattern sequence, -1 = not generated yet */
+    uint8_t* seq_mask; /* [n_q][max_seq]     pattern validity mask (codebooks_patterns.py:130-152) */
+    int32_t* pos;      /* [4] device ints: pos (tokens in the KV cache), rows, batch, text_len */
+    float* noise;      /* [B][n_q][card] Exponential(1) noise, read when sampling.noise_from_buffer != 0 */
+} acb_lm_buffers;
+
+#define ACB_LM_MAX_SPLIT 8
+
+typedef struct {
+    int use_sampling;  /* LMModel.generate(use_sampling, temp, top_k, top_p, cfg_coef), lm.py:421-436 */
+    float temp;
+    int top_k;
+    float top_p;
+    float cfg_coef;
+    uint64_t seed;     /* Philox key for the on-device sampler */
+    int noise_from_buffer; /* 1: take the Exponential(1) noise from acb_lm_buffers.noise / the `noise` argument
+                              (parity tests inject torch's stream); 0: on-device Philox */
+} acb_lm_sampling;
+
+typedef struct acb_lm acb_lm_t;
+
+int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, const acb_lm_buffers* buf, acb_lm_t** out);
+int acb_lm_destroy(acb_lm_t* lm);
+
+/* Start a generation: rows = batch (cross == NULL or cfg disabled) or 2*batch (CFG).  cross is the fp32
+ * condition tensor [rows][text_len][d] the reference's fuser hands to the transformer as
+ * cross_attention_src (conditioners.py:1731-1746; padded / null positions are exact zeros and are still
+ * attended to).  Computes every layer's cross K/V ONCE (the reference recomputes them every step,
+ * transformer.py:355-357), resets pos to 0 and captures the per-step CUDA graph. */
+int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int rows, int text_len, int seq_len,
+                 const acb_lm_sampling* sampling, void* stream);
+
+/* n_steps iterations of the hot loop of LMModel.generate (lm.py:540-565): for the current offset = pos+1,
+ * feed seq[:,:,pos], run the transformer (LMModel.forward lm.py:221-268), CFG-mix, sample
+ * (_sample_next_token lm.py:393-418), apply the pattern mask and write seq[:,:,offset] where it is still -1.
+ * Each step is one CUDA-graph launch; nothing returns to the host. */
+int acb_lm_steps(acb_lm_t* lm, int n_steps, void* stream);
+
+/* Teacher-forced / inspection variant of one step: same as acb_lm_steps(1) and additionally leaves the
+ * CFG-mixed logits [batch][n_q][card] fp32 in logits_out (may be NULL). */
+int acb_lm_step_logits(acb_lm_t* lm, float* logits_out, void* stream);
+
+/* Measurement hook: enqueue ONLY the weight-streaming GEMMs (lm_gemm_kernel) of one decode step, all layers in step
+ * order, so bench.py can time the dominant kernel with CUDA events in isolation.  *n_launches = kernels enqueued. */
+int acb_lm_debug_gemms(acb_lm_t* lm, void* stream, int* n_launches);
+
+/* rows the activation buffers must be padded to for `rows` live rows (8, 16, 32 or 64). */
+int acb_lm_rows_pad(int rows);
+
+/* Number of kernel launches one decode step enqueues (bench.py reports gpu_launches from it). */
+int acb_lm_launches_per_step(const acb_lm_t* lm);
+
+/* Stand-alone sampler (tail of _sample_next_token, lm.py:403-418; utils/utils.py:88-141) for unit tests:
+ * logits [rows][n_q][card] fp32 ([cond; null] rows when rows == 2*batch), noise optional, tokens [batch][n_q]. */
+int acb_sample(const float* logits, const float* noise, int64_t* tokens, int batch, int rows, int n_q, int card,
+               const acb_lm_sampling* sampling, uint64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOCRAFT_B200_H */

@@ -1,0 +1,202 @@
+"""GPU parity: EnCodec kernels (through the C-ABI) vs the CPU oracle and the committed reference golden vectors.
+Tolerances: RVQ indices bit-exact on identical latents (mismatches tolerated only where the oracle's own
+best-vs-second score gap is below fp32 noise, reported); fp32 activations atol 1e-4 (fp32 FMA, different
+summation order than the CPU convs)."""
+import os
+
+import pytest
+import torch
+
+from tests import helpers as H
+from audiocraft_b200 import synth
+from oracle import encodec_oracle as EO
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from audiocraft_b200 import _lib
+    return _lib, _lib.lib()
+
+
+def _dev(t):
+    return t.cuda().contiguous()
+
+
+@pytest.mark.parametrize('cin,cout,k,s,d,causal,L', [
+    (1, 64, 7, 1, 1, False, 500), (64, 32, 3, 1, 1, False, 333), (32, 64, 1, 1, 1, False, 333),
+    (64, 128, 8, 4, 1, False, 1001), (16, 8, 3, 1, 2, False, 77), (8, 16, 10, 5, 1, False, 203),
+    (8, 16, 16, 8, 1, True, 130), (4, 3, 7, 1, 1, True, 50), (4, 2, 7, 1, 1, False, 3), (4, 2, 3, 1, 4, False, 2),
+    (24, 1, 7, 1, 1, False, 1000), (3, 5, 4, 2, 1, True, 1), (130, 70, 3, 1, 1, False, 140),
+])
+def test_conv1d_matches_oracle(cin, cout, k, s, d, causal, L):
+    from audiocraft_b200.encodec import conv_geometry
+    lib, L_ = _lib()
+    g = torch.Generator().manual_seed(cin * 1000 + cout + k + L)
+    x = torch.randn(2, cin, L, generator=g)
+    w = torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    for elu, with_res in [(False, False), (True, True)]:
+        ref = EO.sconv1d(EO.elu(x) if elu else x, w, b, stride=s, dilation=d, causal=causal)
+        res = torch.randn(ref.shape, generator=g) if with_res else None
+        if with_res:
+            ref = ref + res
+        left, tv, tout = conv_geometry(L, k, s, d, causal, True)
+        assert tout == ref.shape[-1]
+        xd, wd, bd = _dev(x), _dev(w.permute(1, 2, 0).reshape(cin * k, cout)), _dev(b)
+        rd = _dev(res) if with_res else None
+        y = torch.empty(2, cout, tout, device='cuda')
+        lib.check(L_.acb_conv1d(lib.ptr(xd), lib.ptr(wd), lib.ptr(bd), lib.ptr(rd), lib.ptr(y), 2, cin, cout, L, tv, tout,
+                                k, s, d, left, 1, int(elu), lib.stream()))
+        torch.testing.assert_close(y.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('cin,cout,s,causal,ratio,L', [
+    (16, 8, 2, False, 1.0, 37), (8, 16, 3, True, 1.0, 20), (32, 16, 4, False, 1.0, 101), (12, 6, 5, False, 1.0, 50),
+    (64, 32, 8, False, 1.0, 50), (8, 4, 4, True, 0.5, 33), (8, 4, 8, True, 0.0, 1), (70, 66, 4, False, 1.0, 70),
+])
+def test_convtr1d_matches_oracle(cin, cout, s, causal, ratio, L):
+    from audiocraft_b200.encodec import convtr_geometry
+    lib, L_ = _lib()
+    g = torch.Generator().manual_seed(cin + cout + s + L)
+    x = torch.randn(2, cin, L, generator=g)
+    w = torch.randn(cin, cout, 2 * s, generator=g) / (2 * cin) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = EO.sconvtr1d(EO.elu(x), w, b, s, causal, ratio)
+    tl, tout = convtr_geometry(L, 2 * s, s, causal, ratio)
+    assert tout == ref.shape[-1] == L * s
+    y = torch.empty(2, cout, tout, device='cuda')
+    lib.check(L_.acb_convtr1d(lib.ptr(_dev(x)), lib.ptr(_dev(w.permute(0, 2, 1))), lib.ptr(_dev(b)), lib.ptr(y), 2, cin,
+                              cout, L, tout, 2 * s, s, tl, 1, lib.stream()))
+    torch.testing.assert_close(y.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_weight_norm_fold_matches_oracle():
+    lib, L_ = _lib()
+    g = torch.Generator().manual_seed(0)
+    for shape in [(64, 32, 3), (5, 1, 7), (128, 64, 16)]:
+        v = torch.randn(shape, generator=g)
+        gg = torch.rand(shape[0], 1, 1, generator=g) + 0.5
+        w = torch.empty(shape, device='cuda')
+        lib.check(L_.acb_weight_norm_fold(lib.ptr(_dev(v)), lib.ptr(_dev(gg)), lib.ptr(w), shape[0], shape[1] * shape[2],
+                                          lib.stream()))
+        torch.testing.assert_close(w.cpu(), EO.fold_weight_norm(gg, v), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('hidden,batch,T,layers', [(64, 3, 20, 2), (512, 2, 9, 1), (1024, 9, 6, 2), (8, 1, 1, 1)])
+def test_lstm_matches_oracle(hidden, batch, T, layers):
+    from audiocraft_b200.encodec import EncodecModel
+    g = torch.Generator().manual_seed(hidden + T)
+    sd = {}
+    bnd = 1.0 / hidden ** 0.5
+    for n in range(layers):
+        for nm, shp in [('weight_ih', (4 * hidden, hidden)), ('weight_hh', (4 * hidden, hidden)), ('bias_ih', (4 * hidden,)),
+                        ('bias_hh', (4 * hidden,))]:
+            sd[f'l.{nm}_l{n}'] = (torch.rand(shp, generator=g) * 2 - 1) * bnd
+    x = torch.randn(batch, hidden, T, generator=g)
+    ref = EO.lstm_block(x, sd, 'l.', layers)
+    m = EncodecModel.__new__(EncodecModel)  # only the LSTM launcher is exercised
+    from audiocraft_b200 import _lib
+    m._lib, m.device, m.launches = _lib.lib(), torch.device('cuda'), 0
+    layer = m._prepare(dict(kind='lstm', prefix='l.', dim=hidden, layers=layers), sd)
+    y = m._lstm(_dev(x), layer)
+    torch.testing.assert_close(y.cpu(), ref, rtol=1e-4, atol=2e-5)
+
+
+def _codes_match(codes_gpu, codes_ref, margins, what):
+    """Bit-exact, except where the oracle's own top-2 gap is below fp32 summation noise (reported)."""
+    neq = codes_gpu != codes_ref
+    if neq.any():
+        # a flipped code changes every later residual: only judge the FIRST differing codebook of each frame
+        first = neq.int().cumsum(1).eq(1) & neq
+        gaps = margins[first]
+        print(f"{what}: {int(first.sum())} near-tie code flips, oracle margins {gaps.tolist()[:8]}")
+        assert (gaps.abs() < 1e-4).all(), f"{what}: RVQ index mismatch with a clear margin"
+
+
+@pytest.mark.parametrize('B,D,T,nq,bins', [(2, 128, 333, 4, 2048), (1, 32, 31, 4, 64), (3, 128, 1, 8, 1024), (1, 128, 4000, 4, 2048)])
+def test_rvq_encode_decode_match_oracle(B, D, T, nq, bins):
+    lib, L_ = _lib()
+    g = torch.Generator().manual_seed(B * D + T)
+    z = torch.randn(B, D, T, generator=g) * 0.4
+    cbs = [torch.randn(bins, D, generator=g) * 0.35 * 0.6 ** k for k in range(nq)]
+    ref, margins = EO.rvq_encode(z, cbs, return_margin=True)
+    cb = _dev(torch.stack(cbs))
+    codes = torch.empty(B, nq, T, dtype=torch.int64, device='cuda')
+    lib.check(L_.acb_rvq_encode(lib.ptr(_dev(z)), lib.ptr(cb), lib.ptr(cb.pow(2).sum(-1).contiguous()), lib.ptr(codes), B, D, T,
+                                nq, bins, lib.stream()))
+    _codes_match(codes.cpu(), ref, margins, 'rvq_encode')
+    out = torch.empty(B, D, T, device='cuda')
+    lib.check(L_.acb_rvq_decode(lib.ptr(_dev(ref)), lib.ptr(cb), lib.ptr(out), B, D, T, nq, bins, lib.stream()))
+    torch.testing.assert_close(out.cpu(), EO.rvq_decode(ref, cbs), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['encodec_tiny', 'encodec_tiny_causal', 'encodec_24k', 'encodec_32k'])
+def test_encodec_model_matches_reference_golden(name):
+    """End to end against the REAL reference's outputs (tests/golden, generated by tests/golden/make_golden.py)."""
+    from audiocraft_b200.encodec import EncodecModel
+    g = torch.load(os.path.join(H.GOLDEN_DIR, f'{name}.pt'), weights_only=False)
+    cfg = synth.ENCODEC_CONFIGS[name]
+    sd = synth.synth_encodec_state_dict(cfg, seed=g['wseed'])
+    x = H.audio_input(cfg, g['batch'], g['length'], g['xseed'])
+    m = EncodecModel(sd, cfg)
+    lat = m.encode_latent(m.preprocess(x.cuda())[0])
+    torch.testing.assert_close(lat.cpu(), g['latent'], rtol=0, atol=1e-4)
+    codes, scale = m.encode(x)
+    assert codes.dtype == torch.int64 and codes.shape == g['codes'].shape
+    # margins from the oracle on the golden latent
+    _, margins = EO.rvq_encode(g['latent'], EO.codebooks_of(sd, cfg['n_q']), return_margin=True)
+    _codes_match(codes.cpu(), g['codes'], margins, name)
+    if g['scale'] is not None:
+        torch.testing.assert_close(scale.cpu(), g['scale'], rtol=1e-5, atol=0)
+    wav = m.decode(g['codes'].cuda(), None if g['scale'] is None else g['scale'].cuda()).cpu()
+    if 'wav' in g:
+        torch.testing.assert_close(wav, g['wav'], rtol=0, atol=1e-4)
+    else:
+        assert wav.shape[-1] == g['wav_len']
+        torch.testing.assert_close(wav[..., :512], g['wav_head'], rtol=0, atol=1e-4)
+        torch.testing.assert_close(wav[..., ::g['wav_stride']], g['wav_strided'], rtol=0, atol=1e-4)
+
+
+def test_encodec_32k_properties_at_size():
+    """Size-independent properties at a bench-like size: length round trip (reference test_encodec_model.py:37-46),
+    batch independence, determinism, and oracle agreement on a slice."""
+    from audiocraft_b200.encodec import EncodecModel
+    cfg = synth.ENCODEC_CONFIGS['encodec_32k']
+    sd = synth.synth_encodec_state_dict(cfg, seed=0)
+    m = EncodecModel(sd, cfg)
+    x = H.audio_input(cfg, 6, 64000 + 123, 3)
+    codes, scale = m.encode(x)
+    assert scale is None and codes.shape == (6, 4, -(-x.shape[-1] // 640))
+    assert int(codes.min()) >= 0 and int(codes.max()) < 2048
+    wav = m.decode(codes)
+    assert wav.shape == (6, 1, codes.shape[-1] * 640) and wav.shape[-1] >= x.shape[-1]
+    assert torch.isfinite(wav).all()
+    codes2, _ = m.encode(x)
+    assert torch.equal(codes, codes2) and torch.equal(wav, m.decode(codes))      # deterministic
+    c1, _ = m.encode(x[2:3])
+    assert torch.equal(c1, codes[2:3])                                           # items are independent
+    torch.testing.assert_close(m.decode(codes[4:5]), wav[4:5], rtol=0, atol=1e-6)
+    o = EO.EncodecOracle(sd, cfg)
+    oc, _ = o.encode(x[:1, :, :16000])
+    gc, _ = m.encode(x[:1, :, :16000])
+    lat = o.encode_latent(x[:1, :, :16000])
+    _, margins = EO.rvq_encode(lat, EO.codebooks_of(sd, 4), return_margin=True)
+    _codes_match(gc.cpu(), oc, margins, 'encodec_32k slice')
+    torch.testing.assert_close(m.decode(oc.cuda()).cpu(), o.decode(oc), rtol=0, atol=1e-4)
+
+
+def test_set_num_codebooks_and_errors():
+    from audiocraft_b200.encodec import EncodecModel
+    cfg = synth.ENCODEC_CONFIGS['encodec_tiny']
+    m = EncodecModel(synth.synth_encodec_state_dict(cfg, 1), cfg)
+    x = H.audio_input(cfg, 1, 400, 1)
+    full, _ = m.encode(x)
+    m.set_num_codebooks(2)
+    part, _ = m.encode(x)
+    assert part.shape[1] == 2 and torch.equal(part, full[:, :2]) and m.num_codebooks == 2 and m.total_codebooks == 4
+    assert m.decode(part).shape == m.decode(full).shape
+    with pytest.raises(AssertionError):
+        m.set_num_codebooks(5)
+    with pytest.raises(AssertionError):
+        m.encode(torch.zeros(1, 3, 100))
