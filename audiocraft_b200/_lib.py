@@ -66,12 +66,13 @@ def lib():
     L.acb_lm_step_logits.argtypes = [vp, vp, vp]
     L.acb_lm_launches_per_step.argtypes = [vp]
     L.acb_lm_rows_pad.argtypes = [ci]
+    L.acb_lm_uses_pdl.argtypes = [vp]
     L.acb_lm_debug_gemms.argtypes = [vp, vp, C.POINTER(ci)]
     L.acb_sample.argtypes = [vp, vp, vp, ci, ci, ci, ci, C.POINTER(LMSampling), C.c_uint64, vp]
     for name in ('acb_weight_norm_fold', 'acb_conv1d', 'acb_convtr1d', 'acb_lstm_recurrent', 'acb_rvq_encode',
                  'acb_rvq_decode', 'acb_lm_create', 'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps',
                  'acb_lm_step_logits', 'acb_lm_launches_per_step', 'acb_lm_rows_pad', 'acb_sample',
-                 'acb_device_sm_count', 'acb_lm_debug_gemms'):
+                 'acb_device_sm_count', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl'):
         getattr(L, name).restype = ci
     _lib = L
     return L
@@ -81,7 +82,7 @@ def lib():
 EXPORTS = ['acb_version', 'acb_last_error', 'acb_device_sm_count', 'acb_weight_norm_fold', 'acb_conv1d', 'acb_convtr1d',
            'acb_lstm_recurrent', 'acb_lstm_state_bytes', 'acb_rvq_encode', 'acb_rvq_decode', 'acb_lm_create',
            'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps', 'acb_lm_step_logits', 'acb_lm_rows_pad',
-           'acb_lm_launches_per_step', 'acb_lm_debug_gemms', 'acb_sample']
+           'acb_lm_launches_per_step', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_sample']
 
 
 def check(rc: int, what: str = ''):

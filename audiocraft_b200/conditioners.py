@@ -94,8 +94,8 @@ class PrecomputedTextConditioner(TextConditioner):
         return {'hidden': hidden, 'attention_mask': mask}
 
     def forward(self, inputs) -> ConditionType:
-        mask = inputs['attention_mask']
         w = self.output_proj.weight
+        mask = inputs['attention_mask'].to(w.device)
         embeds = self.output_proj(inputs['hidden'].to(w))
         return embeds * mask.unsqueeze(-1).to(embeds.dtype), mask
 

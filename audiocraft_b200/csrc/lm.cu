@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include <math.h>
 #include <new>
+#include <stdio.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
@@ -29,36 +31,53 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor is still running; everything before pdl_wait() must only touch memory no earlier
+// kernel of the step writes (weights).  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (UBLKCP in SASS). 16 B aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ float half_round(float v) { return __half2float(__float2half_rn(v)); }
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
 
-__device__ __forceinline__ float block_sum(float v, float* red) {  // red: >= 33 floats
+// Block reductions: every thread returns the full result; red needs >= 32 floats and may be reused right after
+// the call returns only behind another barrier (callers alternate two scratch arrays).
+__device__ __forceinline__ float block_sum(float v, float* red) {
     v = warp_sum(v);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    __syncthreads();
     if (lane == 0) red[warp] = v;
     __syncthreads();
-    if (warp == 0) {
-        float t = lane < nw ? red[lane] : 0.f;
-        t = warp_sum(t);
-        if (lane == 0) red[32] = t;
-    }
-    __syncthreads();
-    return red[32];
+    float t = lane < nw ? red[lane] : 0.f;
+    return warp_sum(t);
 }
 __device__ __forceinline__ float block_max(float v, float* red) {
     v = warp_max(v);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    __syncthreads();
     if (lane == 0) red[warp] = v;
     __syncthreads();
-    if (warp == 0) {
-        float t = lane < nw ? red[lane] : -INFINITY;
-        t = warp_max(t);
-        if (lane == 0) red[32] = t;
-    }
-    __syncthreads();
-    return red[32];
+    float t = lane < nw ? red[lane] : -INFINITY;
+    return warp_max(t);
 }
 
 // ------------------------------------------------------------------------------------------------ embed + sin pos
@@ -67,6 +86,8 @@ __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict_
                                                        const int64_t* __restrict__ seq, const int* __restrict__ P,
                                                        float* __restrict__ x, int d, int n_q, int card, int max_seq,
                                                        int batch, float pos_scale) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x, b = r % batch, pos = P[0];
     __shared__ int tok[16];
     if (threadIdx.x < n_q) {
@@ -87,38 +108,61 @@ __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict_
 
 // ------------------------------------------------------------------------------------------------ residual + LN
 // x[r] += sum_s part[s][r] (fixed order), then h16[r] = LayerNorm(x[r]) * gamma + beta  (eps 1e-5, fp32 statistics).
-constexpr int LN_MAX_PER_THREAD = 16;  // d <= 4096
-__global__ void __launch_bounds__(256) lm_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int nsplit,
-                                                    size_t split_stride, const float* __restrict__ gamma,
-                                                    const float* __restrict__ beta, __half* __restrict__ out, int d) {
-    __shared__ float red[33];
-    const int r = blockIdx.x;
-    float v[LN_MAX_PER_THREAD];
+constexpr int LN_MAX_PER_THREAD = 16;   // kept for the dim bound check (d <= 4096)
+constexpr int LN_THREADS = 256, LN_V4 = 4; // each thread owns up to LN_V4 float4 (d <= 4096)
+__global__ void __launch_bounds__(LN_THREADS) lm_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int nsplit,
+                                                           size_t split_stride, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, __half* __restrict__ out, int d) {
+    __shared__ float red[2][32];
+    const int r = blockIdx.x, d4 = d >> 2;
+    pdl_trigger();
+    pdl_wait();
+    float4* xr = reinterpret_cast<float4*>(x + (size_t)r * d);
+    float4 v[LN_V4];
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < LN_MAX_PER_THREAD; ++j) {
-        const int i = threadIdx.x + j * 256;
-        v[j] = 0.f;
-        if (i < d) {
-            float a = x[(size_t)r * d + i];
-            for (int sp = 0; sp < nsplit; ++sp) a += part[sp * split_stride + (size_t)r * d + i];
-            if (nsplit) x[(size_t)r * d + i] = a;
+    for (int j = 0; j < LN_V4; ++j) {
+        const int i = threadIdx.x + j * LN_THREADS;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < d4) {
+            float4 a = xr[i];
+            float4 pt[ACB_LM_MAX_SPLIT];
+#pragma unroll
+            for (int sp = 0; sp < ACB_LM_MAX_SPLIT; ++sp)   // independent loads, all in flight together
+                pt[sp] = sp < nsplit ? reinterpret_cast<const float4*>(part + sp * split_stride + (size_t)r * d)[i]
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int sp = 0; sp < ACB_LM_MAX_SPLIT; ++sp) {  // fixed summation order
+                a.x += pt[sp].x; a.y += pt[sp].y; a.z += pt[sp].z; a.w += pt[sp].w;
+            }
+            if (nsplit) xr[i] = a;
             v[j] = a;
-            s += a;
+            s += (a.x + a.y) + (a.z + a.w);
         }
     }
-    const float mean = block_sum(s, red) / d;
+    const float mean = block_sum(s, red[0]) / d;
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < LN_MAX_PER_THREAD; ++j) {
-        const int i = threadIdx.x + j * 256;
-        if (i < d) { float c = v[j] - mean; q = fmaf(c, c, q); }
+    for (int j = 0; j < LN_V4; ++j) {
+        const int i = threadIdx.x + j * LN_THREADS;
+        if (i < d4) {
+            float cx = v[j].x - mean, cy = v[j].y - mean, cz = v[j].z - mean, cw = v[j].w - mean;
+            q = fmaf(cx, cx, q); q = fmaf(cy, cy, q); q = fmaf(cz, cz, q); q = fmaf(cw, cw, q);
+        }
     }
-    const float rstd = 1.f / sqrtf(block_sum(q, red) / d + 1e-5f);
+    const float rstd = 1.f / sqrtf(block_sum(q, red[1]) / d + 1e-5f);
 #pragma unroll
-    for (int j = 0; j < LN_MAX_PER_THREAD; ++j) {
-        const int i = threadIdx.x + j * 256;
-        if (i < d) out[(size_t)r * d + i] = __float2half_rn((v[j] - mean) * rstd * gamma[i] + beta[i]);
+    for (int j = 0; j < LN_V4; ++j) {
+        const int i = threadIdx.x + j * LN_THREADS;
+        if (i < d4) {
+            const float4 gm = reinterpret_cast<const float4*>(gamma)[i], bt = reinterpret_cast<const float4*>(beta)[i];
+            __half2 lo = __floats2half2_rn((v[j].x - mean) * rstd * gm.x + bt.x, (v[j].y - mean) * rstd * gm.y + bt.y);
+            __half2 hi = __floats2half2_rn((v[j].z - mean) * rstd * gm.z + bt.z, (v[j].w - mean) * rstd * gm.w + bt.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(out + (size_t)r * d)[i] = pk;
+        }
     }
 }
 
@@ -128,56 +172,75 @@ enum { EPI_PARTIAL = 0, EPI_QKV = 1, EPI_GELU = 2, EPI_F32 = 3, EPI_CROSSKV = 4 
 struct GemmParams {
     const __half* W;  // [N][K] fp16, reference layout
     const __half* X;  // [8*NT][K] fp16, rows >= `rows` are zero
-    int N, K, rows, kb_per_warp;
+    int N, K, rows, kslice;                            // kslice: K elements per CTA (grid.y slices)
     float* out_f32; int ld_out; size_t split_stride;  // PARTIAL / F32
     __half* out_f16;                                   // GELU
     float* q32; __half* kc; __half* vc; int d, H, cache_len; const int* pos;  // QKV / CROSSKV
     int text_len, row0;                                                      // CROSSKV
 };
 
+// CTA = 4 warps, tile = 16 output features x kslice of K.  The CTA's 16 x kslice weight slab is fetched by ONE thread
+// with 16 TMA bulk copies (one per W row, padded pitch => conflict-free fragment reads) BEFORE griddepcontrol.wait, i.e.
+// while the producer of the activations is still running: under PDL the weight stream of kernel n+1 overlaps kernel n.
 template <int NT, int EPI>
-__global__ void __launch_bounds__(256) lm_gemm_kernel(GemmParams p) {
+__global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
     constexpr int U = NT <= 2 ? 4 : (NT <= 4 ? 2 : 1);
     constexpr int RP = 8 * NT + 1;
-    __shared__ float red[8 * 16 * RP];
+    extern __shared__ __align__(128) unsigned char gsm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c4 = lane & 3;
     const int f0 = blockIdx.x * 16;
-    const int nkb = p.K >> 5;
-    const int kb0 = min(nkb, ((int)blockIdx.y * 8 + warp) * p.kb_per_warp);
-    const int kb1 = min(nkb, kb0 + p.kb_per_warp);
+    const int k0 = blockIdx.y * p.kslice;
+    const int ks = min(p.kslice, p.K - k0);          // elements of K this CTA reduces over
+    const int pitch = p.kslice * 2 + 64;             // bytes per staged W row (+64: conflict-free LDS.128)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + 16 * pitch);
+    float* red = reinterpret_cast<float*>(gsm + 16 * pitch + 16);   // [4][16][RP]
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, 16u * (uint32_t)ks * 2u);
+#pragma unroll 1
+        for (int r = 0; r < 16; ++r)
+            bulk_g2s(gsm + r * pitch, p.W + (size_t)(f0 + r) * p.K + k0, (uint32_t)ks * 2u, bar);
+    }
+    pdl_trigger();
+    pdl_wait();   // activations written by the previous kernel are visible from here on
 
     float c[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
 
-    const __half* w0 = p.W + (size_t)(f0 + g) * p.K + 8 * c4;
-    const __half* w1 = w0 + (size_t)8 * p.K;
-    const __half* xr = p.X + (size_t)g * p.K + 8 * c4;
+    const int nkb = ks >> 5;
+    const int kbw = (nkb + 3) >> 2;
+    const int kb0 = min(nkb, warp * kbw), kb1 = min(nkb, kb0 + kbw);
+    const __half* xr = p.X + (size_t)g * p.K + k0 + 8 * c4;
+    const unsigned char* wr0 = gsm + g * pitch + 16 * c4;
+    const unsigned char* wr1 = wr0 + 8 * pitch;
 
+    bool w_ready = false;
     for (int kb = kb0; kb < kb1; kb += U) {
-        uint4 wa[U], wb[U], xv[U][NT];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (kb + u < kb1) {
-                wa[u] = ld_stream_u4(w0 + (size_t)(kb + u) * 32);
-                wb[u] = ld_stream_u4(w1 + (size_t)(kb + u) * 32);
-#pragma unroll
-                for (int j = 0; j < NT; ++j)
-                    xv[u][j] = *reinterpret_cast<const uint4*>(xr + (size_t)(8 * j) * p.K + (size_t)(kb + u) * 32);
-            } else {
-                wa[u] = wb[u] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int j = 0; j < NT; ++j) xv[u][j] = make_uint4(0, 0, 0, 0);
-            }
-        }
+        uint4 xv[U][NT];
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                mma16816(c[j], wa[u].x, wb[u].x, wa[u].y, wb[u].y, xv[u][j].x, xv[u][j].y);
-                mma16816(c[j], wa[u].z, wb[u].z, wa[u].w, wb[u].w, xv[u][j].z, xv[u][j].w);
+            for (int j = 0; j < NT; ++j)
+                xv[u][j] = (kb + u < kb1) ? *reinterpret_cast<const uint4*>(xr + (size_t)(8 * j) * p.K + (size_t)(kb + u) * 32)
+                                          : make_uint4(0, 0, 0, 0);
+        if (!w_ready) { mbar_wait(bar, 0); w_ready = true; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (kb + u < kb1) {
+                const uint4 wa = *reinterpret_cast<const uint4*>(wr0 + (kb + u) * 64);
+                const uint4 wb = *reinterpret_cast<const uint4*>(wr1 + (kb + u) * 64);
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    mma16816(c[j], wa.x, wb.x, wa.y, wb.y, xv[u][j].x, xv[u][j].y);
+                    mma16816(c[j], wa.z, wb.z, wa.w, wb.w, xv[u][j].z, xv[u][j].w);
+                }
             }
+        }
     }
+    if (!w_ready) mbar_wait(bar, 0);   // never leave with a bulk copy in flight
     // cross-warp (split-K inside the CTA) reduction in a fixed order
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -187,12 +250,12 @@ __global__ void __launch_bounds__(256) lm_gemm_kernel(GemmParams p) {
         red[(warp * 16 + g + 8) * RP + 8 * j + 2 * c4 + 1] = c[j][3];
     }
     __syncthreads();
-    for (int idx = tid; idx < 16 * 8 * NT; idx += 256) {
+    for (int idx = tid; idx < 16 * 8 * NT; idx += 128) {
         const int row = idx >> 4, feat = idx & 15;
         if (row >= p.rows) continue;
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) v += red[(w * 16 + feat) * RP + row];
+        for (int w = 0; w < 4; ++w) v += red[(w * 16 + feat) * RP + row];
         const int n = f0 + feat;
         if (EPI == EPI_PARTIAL) {
             p.out_f32[blockIdx.y * p.split_stride + (size_t)row * p.ld_out + n] = v;
@@ -224,12 +287,27 @@ struct AttnParams {
     int H, d, cache_len; const int* pos; int fixed_len; float scale;
 };
 
-__global__ void __launch_bounds__(128) lm_attn_kernel(AttnParams p) {
-    extern __shared__ float sc[];  // [len] scores, then probabilities
-    __shared__ float red[33];
-    __shared__ float osm[4][64];
+// Self attention for one query token: CTA = (row, head), 8 warps, ONE pass over K and V with an online softmax.
+// A warp instruction reads 4 consecutive cache positions (4 x 128 B = 512 contiguous bytes); 8 lanes share a position
+// (8 dims each).  4 positions-groups x 4 unrolled iterations of K and V are in flight per lane before any is consumed.
+constexpr int ATT_WARPS = 8, ATT_UNROLL = 4;
+
+struct OnlineSM { float m, l, acc[8]; };
+__device__ __forceinline__ void osm_merge(OnlineSM& a, float m2, float l2, const float (&acc2)[8]) {
+    const float mn = fmaxf(a.m, m2);
+    const float ca = a.m == -INFINITY ? 0.f : __expf(a.m - mn), cb = m2 == -INFINITY ? 0.f : __expf(m2 - mn);
+    a.l = a.l * ca + l2 * cb;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a.acc[e] = a.acc[e] * ca + acc2[e] * cb;
+    a.m = mn;
+}
+
+__global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
+    __shared__ float wm[ATT_WARPS], wl[ATT_WARPS], wacc[ATT_WARPS][64];
     const int h = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sl = lane & 7, pg = lane >> 3;
+    pdl_trigger();
+    pdl_wait();
     const int n = p.fixed_len > 0 ? p.fixed_len : p.pos[0] + 1;
 
     float q[8];
@@ -237,83 +315,142 @@ __global__ void __launch_bounds__(128) lm_attn_kernel(AttnParams p) {
     for (int e = 0; e < 8; ++e) {
         float a = 0.f;
         for (int s = 0; s < p.q_nsplit; ++s) a += p.q[s * p.q_split_stride + (size_t)row * p.d + h * 64 + sl * 8 + e];
-        q[e] = half_round(a);
+        q[e] = half_round(a) * p.scale;
     }
     const size_t base = ((size_t)row * p.H + h) * p.cache_len * 64 + sl * 8;
     const __half* kb = p.kc + base;
     const __half* vb = p.vc + base;
 
-    float lmax = -INFINITY;
-    for (int p0 = warp * 4 + pg; p0 < n; p0 += 64) {
-        uint4 kv[4];
+    OnlineSM st;
+    st.m = -INFINITY; st.l = 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            kv[u] = (p0 + 16 * u < n) ? ld_stream_u4(kb + (size_t)(p0 + 16 * u) * 64) : make_uint4(0, 0, 0, 0);
+    for (int e = 0; e < 8; ++e) st.acc[e] = 0.f;
+
+    // warp-uniform loop bound (the shuffles need all 32 lanes)
+    for (int pb = warp * 4; pb < n; pb += ATT_WARPS * 4 * ATT_UNROLL) {
+        uint4 kv[ATT_UNROLL], vv[ATT_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < ATT_UNROLL; ++u) {
+            const int pp = pb + u * ATT_WARPS * 4 + pg;
+            if (pp < n) {
+                kv[u] = ld_stream_u4(kb + (size_t)pp * 64);
+                vv[u] = ld_stream_u4(vb + (size_t)pp * 64);
+            } else {
+                kv[u] = vv[u] = make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ATT_UNROLL; ++u) {
+            const int pp = pb + u * ATT_WARPS * 4 + pg;
             const __half2* k2 = reinterpret_cast<const __half2*>(&kv[u]);
             float s = 0.f;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float2 f = __half22float2(k2[e]);
+                const float2 f = __half22float2(k2[e]);
                 s = fmaf(q[2 * e], f.x, s);
                 s = fmaf(q[2 * e + 1], f.y, s);
             }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             s += __shfl_xor_sync(0xffffffffu, s, 4);
-            const int pp = p0 + 16 * u;
             if (pp < n) {
-                s *= p.scale;
-                if (sl == 0) sc[pp] = s;
-                lmax = fmaxf(lmax, s);
+                const float mn = fmaxf(st.m, s);
+                const float corr = __expf(st.m - mn);   // exp(-inf) = 0 on the first position
+                const float pw = __expf(s - mn);
+                st.l = st.l * corr + pw;
+                const __half2* v2 = reinterpret_cast<const __half2*>(&vv[u]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(v2[e]);
+                    st.acc[2 * e] = fmaf(pw, f.x, st.acc[2 * e] * corr);
+                    st.acc[2 * e + 1] = fmaf(pw, f.y, st.acc[2 * e + 1] * corr);
+                }
+                st.m = mn;
             }
         }
     }
-    const float m = block_max(lmax, red);  // (block_max's barriers also publish sc[])
-    float lsum = 0.f;
-    for (int i = tid; i < n; i += 128) {
-        float e = expf(sc[i] - m);
-        sc[i] = e;
-        lsum += e;
-    }
-    const float denom = block_sum(lsum, red);
-
-    float acc[8];
+    // merge the 4 position groups of the warp, then the warps
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int p0 = warp * 4 + pg; p0 < n; p0 += 64) {
-        uint4 vv[4];
+    for (int o = 8; o <= 16; o <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, st.m, o), l2 = __shfl_xor_sync(0xffffffffu, st.l, o);
+        float a2[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            vv[u] = (p0 + 16 * u < n) ? ld_stream_u4(vb + (size_t)(p0 + 16 * u) * 64) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int pp = p0 + 16 * u;
-            const float w = pp < n ? sc[pp] : 0.f;
-            const __half2* v2 = reinterpret_cast<const __half2*>(&vv[u]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 f = __half22float2(v2[e]);
-                acc[2 * e] = fmaf(w, f.x, acc[2 * e]);
-                acc[2 * e + 1] = fmaf(w, f.y, acc[2 * e + 1]);
-            }
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+        for (int e = 0; e < 8; ++e) a2[e] = __shfl_xor_sync(0xffffffffu, st.acc[e], o);
+        osm_merge(st, m2, l2, a2);
     }
     if (pg == 0) {
+        if (sl == 0) { wm[warp] = st.m; wl[warp] = st.l; }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) osm[warp][sl * 8 + e] = acc[e];
+        for (int e = 0; e < 8; ++e) wacc[warp][sl * 8 + e] = st.acc[e];
     }
     __syncthreads();
     if (tid < 64) {
-        float o = (osm[0][tid] + osm[1][tid]) + (osm[2][tid] + osm[3][tid]);
-        p.out[(size_t)row * p.d + h * 64 + tid] = __float2half_rn(o / denom);
+        float mx = wm[0];
+#pragma unroll
+        for (int w = 1; w < ATT_WARPS; ++w) mx = fmaxf(mx, wm[w]);
+        float l = 0.f, o = 0.f;
+#pragma unroll
+        for (int w = 0; w < ATT_WARPS; ++w) {
+            const float cw = wm[w] == -INFINITY ? 0.f : __expf(wm[w] - mx);
+            l = fmaf(wl[w], cw, l);
+            o = fmaf(wacc[w][tid], cw, o);
+        }
+        p.out[(size_t)row * p.d + h * 64 + tid] = __float2half_rn(o / l);
     }
+}
+
+// Cross attention over the (short) text condition: one WARP per (row, head), lane = text position for the scores,
+// lane = 2 output dims for the weighted sum.  K/V were computed once per generate() (acb_lm_begin).
+__global__ void __launch_bounds__(256) lm_cross_attn_kernel(AttnParams p, int rows) {
+    __shared__ float qs[8][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * 8 + warp;          // (row, head) index
+    pdl_trigger();
+    pdl_wait();
+    if (pair >= rows * p.H) return;                  // warp-uniform
+    const int row = pair / p.H, h = pair % p.H, n = p.fixed_len;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        float a = 0.f;
+        for (int s = 0; s < p.q_nsplit; ++s) a += p.q[s * p.q_split_stride + (size_t)row * p.d + h * 64 + lane * 2 + e];
+        qs[warp][lane * 2 + e] = half_round(a) * p.scale;
+    }
+    __syncwarp();
+    const size_t base = ((size_t)row * p.H + h) * p.cache_len * 64;
+    float mx = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int t0 = 0; t0 < n; t0 += 32) {             // chunks of 32 text positions (online softmax across chunks)
+        const int t = t0 + lane;
+        float s = -INFINITY;
+        if (t < n) {
+            const uint4* kr = reinterpret_cast<const uint4*>(p.kc + base + (size_t)t * 64);
+            s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 kk = kr[c];
+                const __half2* k2 = reinterpret_cast<const __half2*>(&kk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(k2[e]);
+                    s = fmaf(qs[warp][c * 8 + 2 * e], f.x, s);
+                    s = fmaf(qs[warp][c * 8 + 2 * e + 1], f.y, s);
+                }
+            }
+        }
+        const float cm = fmaxf(mx, warp_max(s));
+        const float corr = mx == -INFINITY ? 0.f : __expf(mx - cm);
+        const float pw = t < n ? __expf(s - cm) : 0.f;
+        l = l * corr + warp_sum(pw);
+        o0 *= corr; o1 *= corr;
+        const int cnt = min(32, n - t0);
+        for (int j = 0; j < cnt; ++j) {
+            const float wj = __shfl_sync(0xffffffffu, pw, j);
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(p.vc + base + (size_t)(t0 + j) * 64 + lane * 2));
+            o0 = fmaf(wj, f.x, o0);
+            o1 = fmaf(wj, f.y, o1);
+        }
+        mx = cm;
+    }
+    *reinterpret_cast<__half2*>(p.out + (size_t)row * p.d + h * 64 + lane * 2) = __floats2half2_rn(o0 / l, o1 / l);
 }
 
 // ------------------------------------------------------------------------------------------------ sampling
@@ -341,7 +478,7 @@ struct SampleParams {
     const float* logits;  // [rows][n_q*card]
     const float* noise;   // [batch][n_q][card] or NULL
     float* logits_out;    // [batch][n_q][card] CFG-mixed logits or NULL
-    int64_t* seq; const uint8_t* seq_mask; const int* pos; int max_seq;  // in-loop write-back (seq may be NULL)
+    int64_t* seq; const uint8_t* seq_mask; int* pos; int max_seq;  // in-loop write-back (seq may be NULL)
     int64_t* tokens;      // [batch][n_q] stand-alone output (may be NULL)
     int batch, rows, n_q, card, NP;
     int use_sampling, top_k; float temp, top_p, cfg_coef; uint64_t seed; uint32_t step;
@@ -355,7 +492,7 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
     float* pr = sm;                 // [card] logits -> probabilities
     float* sv = pr + p.card;        // [NP] sort values
     int* si = (int*)(sv + p.NP);    // [NP] sort indices
-    __shared__ float red[33];
+    __shared__ float red[3][32];
     __shared__ float bestv[32];
     __shared__ int besti[32];
     __shared__ float s_scalar;
@@ -364,7 +501,10 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
     const bool cfg = p.rows == 2 * p.batch;
     const float* lc = p.logits + ((size_t)b * p.n_q + k) * card;
     const float* lu = p.logits + ((size_t)(p.batch + b) * p.n_q + k) * card;
-    const uint32_t step = p.pos ? (uint32_t)p.pos[0] : p.step;
+    pdl_trigger();
+    pdl_wait();
+    const int cur_pos = p.pos ? p.pos[0] : 0;   // read once: the last block to finish advances it (below)
+    const uint32_t step = p.pos ? (uint32_t)cur_pos : p.step;
 
     for (int i = tid; i < card; i += nt) {
         float l = lc[i];
@@ -379,10 +519,10 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
     if (sampling) {
         float lm = -INFINITY;
         for (int i = tid; i < card; i += nt) { float l = pr[i] / p.temp; pr[i] = l; lm = fmaxf(lm, l); }
-        const float m = block_max(lm, red);
+        const float m = block_max(lm, red[0]);
         float ls = 0.f;
         for (int i = tid; i < card; i += nt) { float e = expf(pr[i] - m); pr[i] = e; ls += e; }
-        const float s = block_sum(ls, red);
+        const float s = block_sum(ls, red[1]);
         for (int i = tid; i < card; i += nt) pr[i] = pr[i] / s;
         __syncthreads();
         const int kk = p.top_k > card ? card : p.top_k;
@@ -416,7 +556,7 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
                 __syncthreads();
                 float ls2 = 0.f;
                 for (int i = tid; i < card; i += nt) ls2 += sv[i];
-                const float s2 = block_sum(ls2, red);
+                const float s2 = block_sum(ls2, red[2]);
                 for (int i = tid; i < card; i += nt) pr[i] = sv[i] / s2;  // pr now lives in sorted space
                 sorted_space = true;
                 __syncthreads();
@@ -427,7 +567,7 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
                 const float kth = s_scalar;
                 float ls2 = 0.f;
                 for (int i = tid; i < card; i += nt) { float v = pr[i] >= kth ? pr[i] : 0.f; pr[i] = v; ls2 += v; }
-                const float s2 = block_sum(ls2, red);
+                const float s2 = block_sum(ls2, red[2]);
                 for (int i = tid; i < card; i += nt) pr[i] = pr[i] / s2;
                 __syncthreads();
             }
@@ -462,17 +602,19 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
         int tok = sorted_space ? si[bi] : bi;
         if (p.tokens) p.tokens[(size_t)b * p.n_q + k] = tok;
         if (p.seq) {
-            const int off = p.pos[0] + 1;
+            const int off = cur_pos + 1;
             if (off < p.max_seq) {
                 if (!p.seq_mask[(size_t)k * p.max_seq + off]) tok = card;            // lm.py:555-556
                 int64_t* dst = p.seq + ((size_t)b * p.n_q + k) * p.max_seq + off;
                 if (*dst == -1) *dst = tok;                                           // lm.py:559-562
             }
+            // the last (b, k) block to get here advances the position: pos[1] counts finished blocks
+            __threadfence();
+            const int done = atomicAdd(p.pos + 1, 1);
+            if (done == (int)(gridDim.x * gridDim.y) - 1) { p.pos[1] = 0; p.pos[0] = cur_pos + 1; }
         }
     }
 }
-
-__global__ void lm_advance_kernel(int* P) { P[0] += 1; }
 
 __global__ void lm_f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n_valid, size_t n_total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,46 +633,104 @@ struct acb_lm {
     int batch = 0, rows = 0, rows_pad = 0, text_len = 0, seq_len = 0, sms = 148;
     int launches = 0;
     bool has_cross = false;
+    bool pdl = true;          // programmatic dependent launch between the kernels of a step
 };
+
+// Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its
+// predecessor in the stream is still running and synchronises itself with griddepcontrol.wait.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                            Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define ACB_LAUNCH(...) ACB_CHECK_CUDA(launch_k(__VA_ARGS__))
 
 static int nt_for_rows(int rows) { return rows <= 8 ? 1 : (rows <= 16 ? 2 : (rows <= 32 ? 4 : 8)); }
 
+static size_t gemm_smem_bytes(int nt, int kslice) {
+    return (size_t)16 * (kslice * 2 + 64) + 16 + (size_t)4 * 16 * (8 * nt + 1) * sizeof(float);
+}
+
 template <int EPI>
-static int launch_gemm(int nt, const GemmParams& p, int nsplit, cudaStream_t s) {
+static int launch_gemm(int nt, const GemmParams& p, int nsplit, cudaStream_t s, bool pdl) {
     dim3 grid(p.N / 16, nsplit);
+    const size_t smem = gemm_smem_bytes(nt, p.kslice);
     switch (nt) {
-        case 1: lm_gemm_kernel<1, EPI><<<grid, 256, 0, s>>>(p); break;
-        case 2: lm_gemm_kernel<2, EPI><<<grid, 256, 0, s>>>(p); break;
-        case 4: lm_gemm_kernel<4, EPI><<<grid, 256, 0, s>>>(p); break;
-        default: lm_gemm_kernel<8, EPI><<<grid, 256, 0, s>>>(p); break;
+        case 1: ACB_LAUNCH(lm_gemm_kernel<1, EPI>, grid, dim3(128), smem, s, pdl, p); break;
+        case 2: ACB_LAUNCH(lm_gemm_kernel<2, EPI>, grid, dim3(128), smem, s, pdl, p); break;
+        case 4: ACB_LAUNCH(lm_gemm_kernel<4, EPI>, grid, dim3(128), smem, s, pdl, p); break;
+        default: ACB_LAUNCH(lm_gemm_kernel<8, EPI>, grid, dim3(128), smem, s, pdl, p); break;
     }
-    ACB_LAUNCH_CHECK();
     return ACB_OK;
 }
 
-// number of K splits so that the weight matrix is spread over >= 2 CTAs per SM (no empty splits)
-static int pick_split(int N, int K, int sms, bool allow) {
-    if (!allow) return 1;
-    int tiles = N / 16, nkb = K / 32;
-    int s = acb_ceil_div(2 * sms, tiles);
-    s = max(1, min(s, ACB_LM_MAX_SPLIT));
-    s = min(s, max(1, nkb / 8));
-    int kbpw = acb_ceil_div(nkb, 8 * s);
-    return acb_ceil_div(nkb, 8 * kbpw);
+template <int NT, int EPI>
+static cudaError_t gemm_attr_one() {
+    cudaError_t e = cudaFuncSetAttribute(lm_gemm_kernel<NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lm_gemm_kernel<NT, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+template <int EPI>
+static cudaError_t gemm_attr_all() {
+    cudaError_t e;
+    if ((e = gemm_attr_one<1, EPI>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_one<2, EPI>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_one<4, EPI>()) != cudaSuccess) return e;
+    return gemm_attr_one<8, EPI>();
 }
 
-static GemmParams base_gemm(const void* W, const void* X, int N, int K, int rows, int nsplit) {
+// K-slices per GEMM: the slab a CTA stages (16 x kslice fp16) must fit ~64 KB of shared memory, and when the
+// consumer can reduce partial sums (allow_split) the matrix is cut further until there are >= 2 CTAs per SM.
+// Returns nsplit (grid.y) and sets *kslice (a multiple of 32 elements).
+static int pick_split(int N, int K, int sms, bool allow_split, int* kslice) {
+    const int nkb = K / 32, tiles = N / 16;
+    int ns = 1;
+    if (allow_split) {
+        ns = max(acb_ceil_div(K, 1536), acb_ceil_div(2 * sms, tiles));
+        ns = max(1, min(min(ns, ACB_LM_MAX_SPLIT), nkb / 2 > 0 ? nkb / 2 : 1));
+    }
+    int kbs = acb_ceil_div(nkb, ns);
+    ns = acb_ceil_div(nkb, kbs);   // no empty slices
+    *kslice = kbs * 32;
+    return ns;
+}
+
+static GemmParams base_gemm(const void* W, const void* X, int N, int K, int rows, int kslice) {
     GemmParams p{};
     p.W = (const __half*)W;
     p.X = (const __half*)X;
-    p.N = N; p.K = K; p.rows = rows;
-    p.kb_per_warp = acb_ceil_div(K / 32, 8 * nsplit);
+    p.N = N; p.K = K; p.rows = rows; p.kslice = kslice;
     return p;
 }
 
 #define ACB_TRY(expr) do { int rc_ = (expr); if (rc_ != ACB_OK) return rc_; } while (0)
 
-static int enqueue_step(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only = false) {
+// ACB_DEBUG=1: synchronise and report after every launch of a directly-enqueued step (not during graph capture).
+static bool acb_debug_on() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ACB_DEBUG"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+static int acb_dbg(cudaStream_t s, bool capturing, const char* what, int layer) {
+    if (!acb_debug_on() || capturing) return ACB_OK;
+    fprintf(stderr, "[acb] %s layer %d ... ", what, layer); fflush(stderr);
+    cudaError_t e = cudaStreamSynchronize(s);
+    fprintf(stderr, "%s\n", cudaGetErrorString(e)); fflush(stderr);
+    if (e != cudaSuccess) { acb_set_error("%s (layer %d): %s", what, layer, cudaGetErrorString(e)); return ACB_ERR_CUDA; }
+    return ACB_OK;
+}
+#define DBG(what, layer) ACB_TRY(acb_dbg(s, capturing, what, layer))
+
+static int enqueue_step(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only = false,
+                        bool capturing = false) {
     const acb_lm_config& c = lm->cfg;
     const acb_lm_buffers& B = lm->buf;
     const int d = c.dim, ffn = c.ffn_dim, L = c.num_layers, H = c.num_heads, rows = lm->rows, nt = nt_for_rows(rows);
@@ -538,108 +738,100 @@ static int enqueue_step(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_la
     const size_t kv_layer = (size_t)c.max_rows * H * c.max_seq * 64;
     const size_t ckv_layer = (size_t)c.max_rows * H * c.max_text * 64;
     const float scale = 1.0f / sqrtf(64.f);
-    int nl = 0;
+    const bool pdl = lm->pdl;
+    int nl = 0, ks = 0;
 
     if (!gemms_only) {
-        lm_embed_kernel<<<rows, 256, 0, s>>>((const __half*)lm->w.emb, lm->w.inv_freq, B.seq, B.pos, B.x, d, c.n_q, c.card,
-                                             c.max_seq, lm->batch, c.pos_scale);
-        ACB_LAUNCH_CHECK(); ++nl;
+        ACB_LAUNCH(lm_embed_kernel, dim3(rows), dim3(256), 0, s, pdl, (const __half*)lm->w.emb, lm->w.inv_freq,
+                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale);
+        ++nl;
+        DBG("lm_embed_kernel", -1);
     }
     int pending = 0;  // split-K partial sums waiting to be folded into x by the next LN
+    auto ln_launch = [&](const float* gamma, const float* beta, int layer) -> int {
+        if (gemms_only) return ACB_OK;
+        ACB_LAUNCH(lm_ln_kernel, dim3(rows), dim3(256), 0, s, pdl, B.x, (const float*)B.part, pending, part_stride, gamma, beta,
+                   (__half*)B.h16, d);
+        ++nl;
+        DBG("lm_ln_kernel", layer);
+        return ACB_OK;
+    };
+    auto partial_gemm = [&](const __half* W, const void* X, int N, int K, int layer) -> int {
+        const int ns = pick_split(N, K, lm->sms, true, &ks);
+        GemmParams p = base_gemm(W, X, N, K, rows, ks);
+        p.out_f32 = B.part; p.ld_out = N; p.split_stride = part_stride;
+        ACB_TRY(launch_gemm<EPI_PARTIAL>(nt, p, ns, s, pdl));
+        ++nl;
+        DBG("gemm_EPI_PARTIAL", layer);
+        pending = ns;
+        return ACB_OK;
+    };
     for (int l = 0; l < L; ++l) {
         const float* ln = lm->w.ln + (size_t)l * 6 * d;
         // --- self attention
-        if (!gemms_only) {
-            lm_ln_kernel<<<rows, 256, 0, s>>>(B.x, B.part, pending, part_stride, ln, ln + d, (__half*)B.h16, d);
-            ACB_LAUNCH_CHECK(); ++nl;
-        }
+        ACB_TRY(ln_launch(ln, ln + d, l));
         {
-            GemmParams p = base_gemm((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, B.h16, 3 * d, d, rows, 1);
+            pick_split(3 * d, d, lm->sms, false, &ks);
+            GemmParams p = base_gemm((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, B.h16, 3 * d, d, rows, ks);
             p.q32 = B.q32; p.kc = (__half*)B.k_cache + l * kv_layer; p.vc = (__half*)B.v_cache + l * kv_layer;
             p.d = d; p.H = H; p.cache_len = c.max_seq; p.pos = B.pos;
-            ACB_TRY(launch_gemm<EPI_QKV>(nt, p, 1, s)); ++nl;
+            ACB_TRY(launch_gemm<EPI_QKV>(nt, p, 1, s, pdl)); ++nl;
+            DBG("gemm_EPI_QKV", l);
         }
         if (!gemms_only) {
             AttnParams a{B.q32, 1, 0, (__half*)B.k_cache + l * kv_layer, (__half*)B.v_cache + l * kv_layer, (__half*)B.a16,
                          H, d, c.max_seq, B.pos, 0, scale};
-            lm_attn_kernel<<<dim3(H, rows), 128, (size_t)c.max_seq * sizeof(float), s>>>(a);
-            ACB_LAUNCH_CHECK(); ++nl;
+            ACB_LAUNCH(lm_attn_kernel, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            ++nl;
+            DBG("lm_attn_kernel", l);
         }
-        {
-            const int ns = pick_split(d, d, lm->sms, true);
-            GemmParams p = base_gemm((const __half*)lm->w.w_o + (size_t)l * d * d, B.a16, d, d, rows, ns);
-            p.out_f32 = B.part; p.ld_out = d; p.split_stride = part_stride;
-            ACB_TRY(launch_gemm<EPI_PARTIAL>(nt, p, ns, s)); ++nl;
-            pending = ns;
-        }
+        ACB_TRY(partial_gemm((const __half*)lm->w.w_o + (size_t)l * d * d, B.a16, d, d, l));
         // --- cross attention
         if (lm->has_cross) {
-            if (!gemms_only) {
-                lm_ln_kernel<<<rows, 256, 0, s>>>(B.x, B.part, pending, part_stride, ln + 2 * d, ln + 3 * d, (__half*)B.h16, d);
-                ACB_LAUNCH_CHECK(); ++nl;
-            }
-            const int nsq = pick_split(d, d, lm->sms, true);
-            {
-                GemmParams p = base_gemm((const __half*)lm->w.w_cq + (size_t)l * d * d, B.h16, d, d, rows, nsq);
-                p.out_f32 = B.part; p.ld_out = d; p.split_stride = part_stride;
-                ACB_TRY(launch_gemm<EPI_PARTIAL>(nt, p, nsq, s)); ++nl;
-            }
+            ACB_TRY(ln_launch(ln + 2 * d, ln + 3 * d, l));
+            ACB_TRY(partial_gemm((const __half*)lm->w.w_cq + (size_t)l * d * d, B.h16, d, d, l));
+            const int nsq = pending;
+            pending = 0;   // these partials are the cross-attention queries, not a residual update
             if (!gemms_only) {
                 AttnParams a{B.part, nsq, part_stride, (__half*)B.ck_cache + l * ckv_layer,
                              (__half*)B.cv_cache + l * ckv_layer, (__half*)B.a16, H, d, c.max_text, B.pos, lm->text_len,
                              scale};
-                lm_attn_kernel<<<dim3(H, rows), 128, (size_t)c.max_text * sizeof(float), s>>>(a);
-                ACB_LAUNCH_CHECK(); ++nl;
+                ACB_LAUNCH(lm_cross_attn_kernel, dim3(acb_ceil_div(rows * H, 8)), dim3(256), 0, s, pdl, a, rows);
+                ++nl;
+                DBG("lm_cross_attn_kernel", l);
             }
-            {
-                const int ns = pick_split(d, d, lm->sms, true);
-                GemmParams p = base_gemm((const __half*)lm->w.w_co + (size_t)l * d * d, B.a16, d, d, rows, ns);
-                p.out_f32 = B.part; p.ld_out = d; p.split_stride = part_stride;
-                ACB_TRY(launch_gemm<EPI_PARTIAL>(nt, p, ns, s)); ++nl;
-                pending = ns;
-            }
+            ACB_TRY(partial_gemm((const __half*)lm->w.w_co + (size_t)l * d * d, B.a16, d, d, l));
         }
         // --- feed forward
-        if (!gemms_only) {
-            lm_ln_kernel<<<rows, 256, 0, s>>>(B.x, B.part, pending, part_stride, ln + 4 * d, ln + 5 * d, (__half*)B.h16, d);
-            ACB_LAUNCH_CHECK(); ++nl;
-        }
+        ACB_TRY(ln_launch(ln + 4 * d, ln + 5 * d, l));
         {
-            GemmParams p = base_gemm((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, B.h16, ffn, d, rows, 1);
+            pick_split(ffn, d, lm->sms, false, &ks);
+            GemmParams p = base_gemm((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, B.h16, ffn, d, rows, ks);
             p.out_f16 = (__half*)B.f16; p.ld_out = ffn;
-            ACB_TRY(launch_gemm<EPI_GELU>(nt, p, 1, s)); ++nl;
+            ACB_TRY(launch_gemm<EPI_GELU>(nt, p, 1, s, pdl)); ++nl;
+            DBG("gemm_EPI_GELU", l);
         }
-        {
-            const int ns = pick_split(d, ffn, lm->sms, true);
-            GemmParams p = base_gemm((const __half*)lm->w.w_ff2 + (size_t)l * d * ffn, B.f16, d, ffn, rows, ns);
-            p.out_f32 = B.part; p.ld_out = d; p.split_stride = part_stride;
-            ACB_TRY(launch_gemm<EPI_PARTIAL>(nt, p, ns, s)); ++nl;
-            pending = ns;
-        }
+        ACB_TRY(partial_gemm((const __half*)lm->w.w_ff2 + (size_t)l * d * ffn, B.f16, d, ffn, l));
     }
-    if (!gemms_only) {
-        lm_ln_kernel<<<rows, 256, 0, s>>>(B.x, B.part, pending, part_stride, lm->w.out_norm, lm->w.out_norm + d, (__half*)B.h16, d);
-        ACB_LAUNCH_CHECK(); ++nl;
-    }
+    ACB_TRY(ln_launch(lm->w.out_norm, lm->w.out_norm + d, -1));
     {
         const int N = c.n_q * c.card;
-        GemmParams p = base_gemm(lm->w.heads, B.h16, N, d, rows, 1);
+        pick_split(N, d, lm->sms, false, &ks);
+        GemmParams p = base_gemm(lm->w.heads, B.h16, N, d, rows, ks);
         p.out_f32 = B.logits; p.ld_out = N;
-        ACB_TRY(launch_gemm<EPI_F32>(nt, p, 1, s)); ++nl;
+        ACB_TRY(launch_gemm<EPI_F32>(nt, p, 1, s, pdl)); ++nl;
+        DBG("gemm_EPI_F32", -1);
     }
     if (!gemms_only) {
         int NP = 1;
         while (NP < c.card) NP <<= 1;
-        SampleParams sp{B.logits, lm->samp.noise_from_buffer ? B.noise : nullptr, logits_out, B.seq, B.seq_mask, B.pos, c.max_seq, nullptr, lm->batch, rows,
-                        c.n_q, c.card, NP, lm->samp.use_sampling, lm->samp.top_k, lm->samp.temp, lm->samp.top_p,
-                        lm->samp.cfg_coef, lm->samp.seed, 0};
+        SampleParams sp{B.logits, lm->samp.noise_from_buffer ? B.noise : nullptr, logits_out, B.seq, B.seq_mask, B.pos,
+                        c.max_seq, nullptr, lm->batch, rows, c.n_q, c.card, NP, lm->samp.use_sampling, lm->samp.top_k,
+                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0};
         size_t smem = ((size_t)c.card + 2 * (size_t)NP) * sizeof(float);
-        lm_sample_kernel<<<dim3(c.n_q, lm->batch), 1024, smem, s>>>(sp);
-        ACB_LAUNCH_CHECK(); ++nl;
-    }
-    if (!gemms_only) {
-        lm_advance_kernel<<<1, 1, 0, s>>>(B.pos);
-        ACB_LAUNCH_CHECK(); ++nl;
+        ACB_LAUNCH(lm_sample_kernel, dim3(c.n_q, lm->batch), dim3(1024), smem, s, pdl, sp);
+        ++nl;
+        DBG("lm_sample_kernel", -1);
     }
     if (n_launch) *n_launch = nl;
     return ACB_OK;
@@ -654,6 +846,7 @@ extern "C" int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, 
     ACB_REQUIRE(cfg->card <= 4096, "acb_lm_create: card %d > 4096 not built", cfg->card);
     ACB_REQUIRE(cfg->max_rows >= 1 && cfg->max_rows <= 64, "acb_lm_create: max_rows %d not in [1,64]", cfg->max_rows);
     ACB_REQUIRE(cfg->max_seq >= 2 && cfg->max_seq <= 12000, "acb_lm_create: max_seq %d out of range", cfg->max_seq);
+    ACB_REQUIRE(cfg->dim <= 2048, "acb_lm_create: dim %d > 2048: the GEMM stages a 16 x dim weight slab per CTA", cfg->dim);
     acb_lm* lm = new (std::nothrow) acb_lm();
     ACB_REQUIRE(lm, "acb_lm_create: out of host memory");
     lm->cfg = *cfg; lm->w = *w; lm->buf = *buf;
@@ -662,7 +855,24 @@ extern "C" int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, 
     cudaDeviceGetAttribute(&lm->sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaStreamCreateWithFlags(&lm->capture_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete lm; acb_set_error("acb_lm_create: cudaStreamCreate: %s", cudaGetErrorString(e)); return ACB_ERR_CUDA; }
-    // sampling kernel needs > 48 KB only for card > ~4000; attention scores for max_seq > 12288
+    // the GEMMs stage up to ~70 KB of weights per CTA; keep the shared-memory carve-out at its maximum for every kernel
+    // of the step so that co-resident kernels (PDL) never force an L1/shared reconfiguration.
+    cudaError_t ea = gemm_attr_all<EPI_PARTIAL>();
+    if (ea == cudaSuccess) ea = gemm_attr_all<EPI_QKV>();
+    if (ea == cudaSuccess) ea = gemm_attr_all<EPI_GELU>();
+    if (ea == cudaSuccess) ea = gemm_attr_all<EPI_F32>();
+    if (ea == cudaSuccess) ea = gemm_attr_all<EPI_CROSSKV>();
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_cross_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_ln_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_embed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_sample_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ea != cudaSuccess) {
+        acb_set_error("acb_lm_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ea));
+        cudaStreamDestroy(lm->capture_stream);
+        delete lm;
+        return ACB_ERR_CUDA;
+    }
     *out = lm;
     return ACB_OK;
 }
@@ -699,7 +909,7 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
     ACB_CHECK_CUDA(cudaMemsetAsync(lm->buf.h16, 0, (size_t)lm->rows_pad * d * sizeof(__half), s));
     ACB_CHECK_CUDA(cudaMemsetAsync(lm->buf.a16, 0, (size_t)lm->rows_pad * d * sizeof(__half), s));
     ACB_CHECK_CUDA(cudaMemsetAsync(lm->buf.f16, 0, (size_t)lm->rows_pad * c.ffn_dim * sizeof(__half), s));
-    int hp[4] = {0, rows, batch, text_len};
+    int hp[4] = {0, 0, batch, text_len};   // pos, finished-block counter of the sampler, (info) batch, text_len
     ACB_CHECK_CUDA(cudaMemcpyAsync(lm->buf.pos, hp, sizeof(hp), cudaMemcpyHostToDevice, s));
     if (lm->has_cross) {
         const size_t M = (size_t)rows * text_len, Mpad = (M + 63) / 64 * 64;
@@ -708,11 +918,13 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
         const size_t ckv_layer = (size_t)c.max_rows * H * c.max_text * 64;
         for (int l = 0; l < c.num_layers; ++l)
             for (size_t r0 = 0; r0 < M; r0 += 64) {
+                int ks = 0;
+                pick_split(2 * d, d, lm->sms, false, &ks);
                 GemmParams p = base_gemm((const __half*)lm->w.w_ckv + (size_t)l * 2 * d * d,
-                                         (const __half*)lm->buf.cross16 + r0 * d, 2 * d, d, (int)min((size_t)64, M - r0), 1);
+                                         (const __half*)lm->buf.cross16 + r0 * d, 2 * d, d, (int)min((size_t)64, M - r0), ks);
                 p.kc = (__half*)lm->buf.ck_cache + l * ckv_layer; p.vc = (__half*)lm->buf.cv_cache + l * ckv_layer;
                 p.d = d; p.H = H; p.cache_len = c.max_text; p.text_len = text_len; p.row0 = (int)r0;
-                ACB_TRY(launch_gemm<EPI_CROSSKV>(8, p, 1, s));
+                ACB_TRY(launch_gemm<EPI_CROSSKV>(8, p, 1, s, false));
             }
     }
     // opt in to large dynamic shared memory where needed
@@ -722,20 +934,31 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
         size_t smem = ((size_t)c.card + 2 * (size_t)NP) * sizeof(float);
         if (smem > 48 * 1024)
             ACB_CHECK_CUDA(cudaFuncSetAttribute(lm_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        size_t asm_ = (size_t)max(c.max_seq, c.max_text) * sizeof(float);
-        if (asm_ > 48 * 1024)
-            ACB_CHECK_CUDA(cudaFuncSetAttribute(lm_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_));
     }
-    // capture one decode step
-    drop_graph(lm);
-    ACB_CHECK_CUDA(cudaStreamBeginCapture(lm->capture_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_step(lm, lm->capture_stream, nullptr, &lm->launches);
-    cudaError_t e = cudaStreamEndCapture(lm->capture_stream, &lm->graph);
-    if (rc != ACB_OK) { drop_graph(lm); return rc; }
-    if (e != cudaSuccess) { acb_set_error("acb_lm_begin: graph capture failed: %s", cudaGetErrorString(e)); drop_graph(lm); return ACB_ERR_CUDA; }
-    ACB_CHECK_CUDA(cudaGraphInstantiate(&lm->exec, lm->graph, 0));
+    // capture one decode step (with programmatic dependent launch edges; plain edges if the driver refuses them)
+    {
+        const char* e = getenv("ACB_NO_PDL");
+        lm->pdl = !(e && e[0] == '1');
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        drop_graph(lm);
+        ACB_CHECK_CUDA(cudaStreamBeginCapture(lm->capture_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_step(lm, lm->capture_stream, nullptr, &lm->launches, false, true);
+        cudaError_t e = cudaStreamEndCapture(lm->capture_stream, &lm->graph);
+        if (rc == ACB_OK && e == cudaSuccess) e = cudaGraphInstantiate(&lm->exec, lm->graph, 0);
+        if (rc == ACB_OK && e == cudaSuccess) return ACB_OK;
+        cudaGetLastError();
+        drop_graph(lm);
+        if (!lm->pdl || attempt == 1) {
+            if (rc == ACB_OK) acb_set_error("acb_lm_begin: graph capture failed: %s", cudaGetErrorString(e));
+            return rc != ACB_OK ? rc : ACB_ERR_CUDA;
+        }
+        lm->pdl = false;   // retry without programmatic edges
+    }
     return ACB_OK;
 }
+
+extern "C" int acb_lm_uses_pdl(const acb_lm_t* lm) { return lm && lm->pdl ? 1 : 0; }
 
 extern "C" int acb_lm_steps(acb_lm_t* lm, int n_steps, void* stream) {
     ACB_REQUIRE(lm && lm->exec, "acb_lm_steps: call acb_lm_begin first");

@@ -187,6 +187,9 @@ int acb_lm_step_logits(acb_lm_t* lm, float* logits_out, void* stream);
  * order, so bench.py can time the dominant kernel with CUDA events in isolation.  *n_launches = kernels enqueued. */
 int acb_lm_debug_gemms(acb_lm_t* lm, void* stream, int* n_launches);
 
+/* 1 if the captured decode step uses programmatic dependent launch edges (ACB_NO_PDL=1 disables them). */
+int acb_lm_uses_pdl(const acb_lm_t* lm);
+
 /* rows the activation buffers must be padded to for `rows` live rows (8, 16, 32 or 64). */
 int acb_lm_rows_pad(int rows);
 

@@ -66,7 +66,8 @@ def test_convtr1d_matches_oracle(cin, cout, s, causal, ratio, L):
     tl, tout = convtr_geometry(L, 2 * s, s, causal, ratio)
     assert tout == ref.shape[-1] == L * s
     y = torch.empty(2, cout, tout, device='cuda')
-    lib.check(L_.acb_convtr1d(lib.ptr(_dev(x)), lib.ptr(_dev(w.permute(0, 2, 1))), lib.ptr(_dev(b)), lib.ptr(y), 2, cin,
+    xd, wd, bd = _dev(x), _dev(w.permute(0, 2, 1)), _dev(b)   # keep the device tensors alive across the launch
+    lib.check(L_.acb_convtr1d(lib.ptr(xd), lib.ptr(wd), lib.ptr(bd), lib.ptr(y), 2, cin,
                               cout, L, tout, 2 * s, s, tl, 1, lib.stream()))
     torch.testing.assert_close(y.cpu(), ref, rtol=1e-4, atol=1e-4)
 
@@ -78,7 +79,8 @@ def test_weight_norm_fold_matches_oracle():
         v = torch.randn(shape, generator=g)
         gg = torch.rand(shape[0], 1, 1, generator=g) + 0.5
         w = torch.empty(shape, device='cuda')
-        lib.check(L_.acb_weight_norm_fold(lib.ptr(_dev(v)), lib.ptr(_dev(gg)), lib.ptr(w), shape[0], shape[1] * shape[2],
+        vd, gd = _dev(v), _dev(gg)
+        lib.check(L_.acb_weight_norm_fold(lib.ptr(vd), lib.ptr(gd), lib.ptr(w), shape[0], shape[1] * shape[2],
                                           lib.stream()))
         torch.testing.assert_close(w.cpu(), EO.fold_weight_norm(gg, v), rtol=1e-5, atol=1e-6)
 
@@ -123,11 +125,13 @@ def test_rvq_encode_decode_match_oracle(B, D, T, nq, bins):
     ref, margins = EO.rvq_encode(z, cbs, return_margin=True)
     cb = _dev(torch.stack(cbs))
     codes = torch.empty(B, nq, T, dtype=torch.int64, device='cuda')
-    lib.check(L_.acb_rvq_encode(lib.ptr(_dev(z)), lib.ptr(cb), lib.ptr(cb.pow(2).sum(-1).contiguous()), lib.ptr(codes), B, D, T,
+    zd, cbn = _dev(z), cb.pow(2).sum(-1).contiguous()
+    lib.check(L_.acb_rvq_encode(lib.ptr(zd), lib.ptr(cb), lib.ptr(cbn), lib.ptr(codes), B, D, T,
                                 nq, bins, lib.stream()))
     _codes_match(codes.cpu(), ref, margins, 'rvq_encode')
     out = torch.empty(B, D, T, device='cuda')
-    lib.check(L_.acb_rvq_decode(lib.ptr(_dev(ref)), lib.ptr(cb), lib.ptr(out), B, D, T, nq, bins, lib.stream()))
+    refd = _dev(ref)
+    lib.check(L_.acb_rvq_decode(lib.ptr(refd), lib.ptr(cb), lib.ptr(out), B, D, T, nq, bins, lib.stream()))
     torch.testing.assert_close(out.cpu(), EO.rvq_decode(ref, cbs), rtol=0, atol=1e-6)
 
 
