@@ -189,7 +189,8 @@ def test_musicgen_api_shapes_and_callbacks():
     cm = load_compression_model('synthetic/encodec_tiny')
     cm.renormalize = False
     cm.set_num_codebooks(4)
-    mg = MusicGen('debug', cm, lm, max_duration=2.0)
+    mg = MusicGen('debug', cm, lm, max_duration=30)   # like the reference's debug model (musicgen.py:76-80)
+    mg.max_duration = 2.0                              # keep the > max_duration windowing case short
     fr = mg.frame_rate
     assert mg.sample_rate == 16000 and mg.audio_channels == 1
     mg.set_generation_params(duration=1.0, extend_stride=0.5, top_k=40)
