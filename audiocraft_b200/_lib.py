@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libaudiocraft_b200.so')
 
 ACB_LM_MAX_SPLIT = 8
+ACB_LM_PLAN_BYTES = 2 << 20
 
 
 class LMConfig(C.Structure):
@@ -26,7 +27,7 @@ class LMWeights(C.Structure):
 
 class LMBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('x', 'h16', 'a16', 'f16', 'q32', 'part', 'logits', 'k_cache', 'v_cache',
-                                           'ck_cache', 'cv_cache', 'cross16', 'seq', 'seq_mask', 'pos', 'noise')]
+                                           'ck_cache', 'cv_cache', 'cross16', 'seq', 'seq_mask', 'pos', 'noise', 'plan')]
 
 
 class LMSampling(C.Structure):

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <new>
+#include <vector>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -616,6 +617,224 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ chain kernel
+// A decode step is a strict dependency chain of ~11 small phases per layer; as separate kernels each phase pays a
+// ~4 us kernel boundary, 4x what its HBM traffic needs.  The chain kernel runs every GEMM / LayerNorm phase that lies
+// between two attention kernels inside ONE persistent kernel: all CTAs are co-resident (2 per SM), phases are
+// separated by a grid barrier (one atomic + an acquire spin, ~1 us), and because a CTA's weight slabs are static it
+// prefetches them with TMA bulk copies TWO GEMM phases ahead, so the HBM weight stream keeps running through
+// barriers and LayerNorm phases.  Activations written by other CTAs of the same launch are read with ld.global.cg
+// (L1 is not coherent across SMs).
+enum { PH_GEMM = 0, PH_LN = 1 };
+struct ChainPhase {
+    int kind;
+    // PH_GEMM
+    const __half* W; const __half* X16; int N, K, kslice, nsplit, epi;
+    float* out_f32; int ld_out; size_t split_stride; __half* out_f16;
+    float* q32; __half* kc; __half* vc; int d, H, cache_len;
+    // PH_LN
+    float* x; const float* part; int ln_nsplit; size_t ln_split_stride; const float* gamma; const float* beta; __half* ln_out;
+};
+struct ChainParams { const ChainPhase* ph; int nph, rows, slab_bytes; unsigned* bar; const int* pos; };
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void chain_issue(const ChainPhase& P, int item, unsigned char* buf, uint64_t* bar) {
+    const int tiles = P.N >> 4, f0 = (item % tiles) << 4, k0 = (item / tiles) * P.kslice;
+    const int ks = min(P.kslice, P.K - k0), pitch = P.kslice * 2 + 64;
+    mbar_expect_tx(bar, 16u * (uint32_t)ks * 2u);
+#pragma unroll 1
+    for (int r = 0; r < 16; ++r) bulk_g2s(buf + r * pitch, P.W + (size_t)(f0 + r) * P.K + k0, (uint32_t)ks * 2u, bar);
+}
+
+template <int NT>
+__device__ __forceinline__ void chain_gemm_item(const ChainPhase& P, int item, const unsigned char* buf, uint64_t* bar,
+                                                uint32_t parity, float* red, int rows, const int* pos) {
+    constexpr int U = NT <= 2 ? 4 : (NT <= 4 ? 2 : 1);
+    constexpr int RP = 8 * NT + 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c4 = lane & 3;
+    const int tiles = P.N >> 4, f0 = (item % tiles) << 4, split = item / tiles, k0 = split * P.kslice;
+    const int ks = min(P.kslice, P.K - k0), pitch = P.kslice * 2 + 64;
+    float c[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+    const int nkb = ks >> 5, kbw = (nkb + 3) >> 2;
+    const int kb0 = min(nkb, warp * kbw), kb1 = min(nkb, kb0 + kbw);
+    const __half* xr = P.X16 + (size_t)g * P.K + k0 + 8 * c4;
+    const unsigned char* wr0 = buf + g * pitch + 16 * c4;
+    const unsigned char* wr1 = wr0 + 8 * pitch;
+    bool ready = false;
+    for (int kb = kb0; kb < kb1; kb += U) {
+        uint4 xv[U][NT];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                xv[u][j] = (kb + u < kb1) ? __ldcg(reinterpret_cast<const uint4*>(xr + (size_t)(8 * j) * P.K + (size_t)(kb + u) * 32))
+                                          : make_uint4(0, 0, 0, 0);
+        if (!ready) { mbar_wait(bar, parity); ready = true; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (kb + u < kb1) {
+                const uint4 wa = *reinterpret_cast<const uint4*>(wr0 + (kb + u) * 64);
+                const uint4 wb = *reinterpret_cast<const uint4*>(wr1 + (kb + u) * 64);
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    mma16816(c[j], wa.x, wb.x, wa.y, wb.y, xv[u][j].x, xv[u][j].y);
+                    mma16816(c[j], wa.z, wb.z, wa.w, wb.w, xv[u][j].z, xv[u][j].w);
+                }
+            }
+        }
+    }
+    if (!ready) mbar_wait(bar, parity);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        red[(warp * 16 + g) * RP + 8 * j + 2 * c4] = c[j][0];
+        red[(warp * 16 + g) * RP + 8 * j + 2 * c4 + 1] = c[j][1];
+        red[(warp * 16 + g + 8) * RP + 8 * j + 2 * c4] = c[j][2];
+        red[(warp * 16 + g + 8) * RP + 8 * j + 2 * c4 + 1] = c[j][3];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 16 * 8 * NT; idx += 128) {
+        const int row = idx >> 4, feat = idx & 15;
+        if (row >= rows) continue;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) v += red[(w * 16 + feat) * RP + row];
+        const int n = f0 + feat;
+        if (P.epi == EPI_PARTIAL) {
+            P.out_f32[split * P.split_stride + (size_t)row * P.ld_out + n] = v;
+        } else if (P.epi == EPI_F32) {
+            P.out_f32[(size_t)row * P.ld_out + n] = v;
+        } else if (P.epi == EPI_GELU) {
+            P.out_f16[(size_t)row * P.ld_out + n] = __float2half_rn(gelu_erf(half_round(v)));
+        } else {  // EPI_QKV
+            if (n < P.d) {
+                P.q32[(size_t)row * P.d + n] = v;
+            } else {
+                const int which = (n - P.d) / P.d, nn = n % P.d, h = nn >> 6, dd = nn & 63;
+                __half* cache = which ? P.vc : P.kc;
+                cache[(((size_t)row * P.H + h) * P.cache_len + pos[0]) * 64 + dd] = __float2half_rn(v);
+            }
+        }
+    }
+    __syncthreads();   // red and the weight buffer may be reused
+}
+
+// residual + LayerNorm of one row by one 128-thread CTA (same arithmetic and summation order as lm_ln_kernel)
+__device__ __forceinline__ void chain_ln_row(const ChainPhase& P, int r, float* red) {
+    constexpr int V4 = 8;   // d <= 4096
+    const int d = P.d, d4 = d >> 2;
+    float4* xr = reinterpret_cast<float4*>(P.x + (size_t)r * d);
+    float4 v[V4];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V4; ++j) {
+        const int i = threadIdx.x + j * 128;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < d4) {
+            float4 a = __ldcg(xr + i);
+            for (int sp = 0; sp < P.ln_nsplit; ++sp) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(P.part + sp * P.ln_split_stride + (size_t)r * d) + i);
+                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+            }
+            if (P.ln_nsplit) xr[i] = a;
+            v[j] = a;
+            s += (a.x + a.y) + (a.z + a.w);
+        }
+    }
+    const float mean = block_sum(s, red) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < V4; ++j) {
+        const int i = threadIdx.x + j * 128;
+        if (i < d4) {
+            float cx = v[j].x - mean, cy = v[j].y - mean, cz = v[j].z - mean, cw = v[j].w - mean;
+            q = fmaf(cx, cx, q); q = fmaf(cy, cy, q); q = fmaf(cz, cz, q); q = fmaf(cw, cw, q);
+        }
+    }
+    const float rstd = 1.f / sqrtf(block_sum(q, red + 32) / d + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < V4; ++j) {
+        const int i = threadIdx.x + j * 128;
+        if (i < d4) {
+            const float4 gm = reinterpret_cast<const float4*>(P.gamma)[i], bt = reinterpret_cast<const float4*>(P.beta)[i];
+            __half2 lo = __floats2half2_rn((v[j].x - mean) * rstd * gm.x + bt.x, (v[j].y - mean) * rstd * gm.y + bt.y);
+            __half2 hi = __floats2half2_rn((v[j].z - mean) * rstd * gm.z + bt.z, (v[j].w - mean) * rstd * gm.w + bt.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(P.ln_out + (size_t)r * d)[i] = pk;
+        }
+    }
+    __syncthreads();   // red reusable
+}
+
+template <int NT>
+__global__ void __launch_bounds__(128) lm_chain_kernel(ChainParams cp) {
+    constexpr int RP = 8 * NT + 1;
+    extern __shared__ __align__(128) unsigned char csm[];
+    unsigned char* buf[2] = {csm, csm + cp.slab_bytes};
+    uint64_t* bars = reinterpret_cast<uint64_t*>(csm + 2 * (size_t)cp.slab_bytes);
+    float* red = reinterpret_cast<float*>(bars + 2);   // max(4*16*RP, 64) floats
+    const int tid = threadIdx.x, cta = blockIdx.x, G = gridDim.x;
+    uint32_t uses[2] = {0u, 0u};
+
+    if (tid == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
+    __syncthreads();
+    // the GEMM phases this CTA will run, and the two first slabs (weights do not depend on earlier kernels)
+    auto next_gemm = [&](int from) { int q = from; while (q < cp.nph && cp.ph[q].kind != PH_GEMM) ++q; return q; };
+    auto prefetch = [&](int ph, int b) {   // first item of GEMM phase `ph` into buffer b (thread 0)
+        if (ph < cp.nph && tid == 0) {
+            const ChainPhase& Q = cp.ph[ph];
+            if (cta < (Q.N >> 4) * Q.nsplit) chain_issue(Q, cta, buf[b], bars + b);
+        }
+    };
+    int g_next = next_gemm(0);
+    prefetch(g_next, 0);
+    int g_next2 = next_gemm(g_next + 1);
+    prefetch(g_next2, 1);
+    pdl_trigger();
+    pdl_wait();
+
+    int cur = 0;
+    for (int ph = 0; ph < cp.nph; ++ph) {
+        const ChainPhase& P = cp.ph[ph];
+        if (P.kind == PH_GEMM) {
+            const int n_items = (P.N >> 4) * P.nsplit;
+            bool first = true;
+            for (int item = cta; item < n_items; item += G) {
+                if (!first && tid == 0) chain_issue(P, item, buf[cur], bars + cur);
+                chain_gemm_item<NT>(P, item, buf[cur], bars + cur, uses[cur] & 1u, red, cp.rows, cp.pos);
+                ++uses[cur];
+                first = false;
+            }
+            // this buffer is free again: fetch the first slab of the GEMM phase after next
+            const int g3 = next_gemm(g_next2 + 1);
+            prefetch(g3, cur);
+            g_next = g_next2; g_next2 = g3;
+            cur ^= 1;
+        } else {
+            if (cta < cp.rows) chain_ln_row(P, cta, red);
+        }
+        if (ph + 1 < cp.nph) {   // grid barrier
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(cp.bar, 1u);
+                const unsigned target = (unsigned)(ph + 1) * (unsigned)G;
+                while (ld_acquire_gpu_u32(cp.bar) < target) { }
+            }
+            __syncthreads();
+        }
+    }
+    (void)RP;
+}
+
 __global__ void lm_f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n_valid, size_t n_total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_total) dst[i] = __float2half_rn(i < n_valid ? src[i] : 0.f);
@@ -634,7 +853,13 @@ struct acb_lm {
     int launches = 0;
     bool has_cross = false;
     bool pdl = true;          // programmatic dependent launch between the kernels of a step
+    bool chain = false;       // GEMM/LN phases between attention kernels run in persistent chain kernels (opt-in)
+    int chain_grid = 0, chain_slab = 0;
+    size_t chain_smem = 0;
+    std::vector<ChainPhase> plan;            // host copy of every chain's phases, in launch order
+    std::vector<int> chain_off, chain_len;   // per chain launch: offset / count into plan
 };
+constexpr size_t ACB_PLAN_COUNTER_BYTES = 4096;   // first bytes of buffers.plan: one barrier counter per chain launch
 
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its
 // predecessor in the stream is still running and synchronises itself with griddepcontrol.wait.
@@ -713,6 +938,124 @@ static GemmParams base_gemm(const void* W, const void* X, int N, int K, int rows
 
 #define ACB_TRY(expr) do { int rc_ = (expr); if (rc_ != ACB_OK) return rc_; } while (0)
 
+template <int NT>
+static cudaError_t chain_attr(size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(lm_chain_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lm_chain_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+template <int NT>
+static cudaError_t chain_occupancy(size_t smem, int* per_sm) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, lm_chain_kernel<NT>, 128, smem);
+}
+
+// Build the phase lists of every chain launch of one decode step for the current (rows, cross) configuration and
+// upload them to the caller-owned plan buffer.  Chains are cut at the attention kernels:
+//   chain 0            : LN1(0) QKV(0)
+//   per layer (cross)  : [O LNc CQ]   and   [CO LN2 FFN1 FFN2 LN1(l+1) QKV(l+1)]   (last layer: ... LNout heads)
+//   per layer (no cross): [O LN2 FFN1 FFN2 LN1(l+1) QKV(l+1)]
+static int build_chain_plan(acb_lm* lm, cudaStream_t s) {
+    const acb_lm_config& c = lm->cfg;
+    const acb_lm_buffers& B = lm->buf;
+    const int d = c.dim, ffn = c.ffn_dim, L = c.num_layers, H = c.num_heads, rows = lm->rows, nt = nt_for_rows(rows);
+    const size_t part_stride = (size_t)lm->rows_pad * d;
+    const size_t kv_layer = (size_t)c.max_rows * H * c.max_seq * 64;
+    const int max_kslice = d <= 1536 ? 1536 : 2048;
+    lm->chain_slab = 16 * (max_kslice * 2 + 64);
+    lm->chain_smem = 2 * (size_t)lm->chain_slab + 2 * sizeof(uint64_t) + (size_t)max(4 * 16 * (8 * nt + 1), 64) * sizeof(float);
+    cudaError_t e;
+    int per_sm = 0;
+    switch (nt) {
+        case 1: e = chain_attr<1>(lm->chain_smem); if (e == cudaSuccess) e = chain_occupancy<1>(lm->chain_smem, &per_sm); break;
+        case 2: e = chain_attr<2>(lm->chain_smem); if (e == cudaSuccess) e = chain_occupancy<2>(lm->chain_smem, &per_sm); break;
+        case 4: e = chain_attr<4>(lm->chain_smem); if (e == cudaSuccess) e = chain_occupancy<4>(lm->chain_smem, &per_sm); break;
+        default: e = chain_attr<8>(lm->chain_smem); if (e == cudaSuccess) e = chain_occupancy<8>(lm->chain_smem, &per_sm); break;
+    }
+    ACB_CHECK_CUDA(e);
+    ACB_REQUIRE(per_sm >= 1, "chain kernel does not fit an SM (%zu B smem)", lm->chain_smem);
+    lm->chain_grid = lm->sms * min(per_sm, 2);   // every CTA must be resident: the phases synchronise with a spin barrier
+    const int G = lm->chain_grid;
+
+    lm->plan.clear(); lm->chain_off.clear(); lm->chain_len.clear();
+    int pending = 0;
+    auto begin_chain = [&]() { lm->chain_off.push_back((int)lm->plan.size()); };
+    auto end_chain = [&]() { lm->chain_len.push_back((int)lm->plan.size() - lm->chain_off.back()); };
+    auto ln = [&](const float* gamma, const float* beta) {
+        ChainPhase P{};
+        P.kind = PH_LN; P.d = d; P.x = B.x; P.part = B.part; P.ln_nsplit = pending; P.ln_split_stride = part_stride;
+        P.gamma = gamma; P.beta = beta; P.ln_out = (__half*)B.h16;
+        lm->plan.push_back(P);
+        pending = 0;
+    };
+    auto gemm = [&](const __half* W, const void* X16, int N, int K, int epi, bool split) -> ChainPhase& {
+        ChainPhase P{};
+        P.kind = PH_GEMM; P.W = W; P.X16 = (const __half*)X16; P.N = N; P.K = K; P.epi = epi; P.d = d; P.H = H;
+        const int nkb = K / 32, tiles = N / 16;
+        int ns = acb_ceil_div(K, max_kslice);
+        if (split) ns = max(ns, min(G / tiles, ACB_LM_MAX_SPLIT));
+        ns = max(1, min(ns, nkb));
+        const int kbs = acb_ceil_div(nkb, ns);
+        P.nsplit = acb_ceil_div(nkb, kbs);
+        P.kslice = kbs * 32;
+        if (epi == EPI_PARTIAL) { P.out_f32 = B.part; P.ld_out = N; P.split_stride = part_stride; }
+        lm->plan.push_back(P);
+        return lm->plan.back();
+    };
+    auto qkv_or_heads = [&](int l) {   // LN1(l) + QKV(l), or the output norm + heads after the last layer
+        if (l < L) {
+            const float* lnp = lm->w.ln + (size_t)l * 6 * d;
+            ln(lnp, lnp + d);
+            ChainPhase& P = gemm((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, B.h16, 3 * d, d, EPI_QKV, false);
+            P.q32 = B.q32; P.kc = (__half*)B.k_cache + l * kv_layer; P.vc = (__half*)B.v_cache + l * kv_layer; P.cache_len = c.max_seq;
+        } else {
+            ln(lm->w.out_norm, lm->w.out_norm + d);
+            ChainPhase& P = gemm((const __half*)lm->w.heads, B.h16, c.n_q * c.card, d, EPI_F32, false);
+            P.out_f32 = B.logits; P.ld_out = c.n_q * c.card;
+        }
+    };
+    begin_chain(); qkv_or_heads(0); end_chain();
+    for (int l = 0; l < L; ++l) {
+        const float* lnp = lm->w.ln + (size_t)l * 6 * d;
+        begin_chain();
+        pending = gemm((const __half*)lm->w.w_o + (size_t)l * d * d, B.a16, d, d, EPI_PARTIAL, true).nsplit;
+        if (lm->has_cross) {
+            ln(lnp + 2 * d, lnp + 3 * d);
+            gemm((const __half*)lm->w.w_cq + (size_t)l * d * d, B.h16, d, d, EPI_PARTIAL, true);   // partial queries
+            end_chain();
+            begin_chain();
+            pending = gemm((const __half*)lm->w.w_co + (size_t)l * d * d, B.a16, d, d, EPI_PARTIAL, true).nsplit;
+        }
+        ln(lnp + 4 * d, lnp + 5 * d);
+        {
+            ChainPhase& P = gemm((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, B.h16, ffn, d, EPI_GELU, false);
+            P.out_f16 = (__half*)B.f16; P.ld_out = ffn;
+        }
+        pending = gemm((const __half*)lm->w.w_ff2 + (size_t)l * d * ffn, B.f16, d, ffn, EPI_PARTIAL, true).nsplit;
+        qkv_or_heads(l + 1);
+        end_chain();
+    }
+    const size_t bytes = lm->plan.size() * sizeof(ChainPhase);
+    ACB_REQUIRE(lm->chain_off.size() * sizeof(unsigned) <= ACB_PLAN_COUNTER_BYTES && ACB_PLAN_COUNTER_BYTES + bytes <= ACB_LM_PLAN_BYTES,
+                "chain plan (%zu B) does not fit the plan buffer", bytes);
+    ACB_CHECK_CUDA(cudaMemcpyAsync((unsigned char*)B.plan + ACB_PLAN_COUNTER_BYTES, lm->plan.data(), bytes, cudaMemcpyHostToDevice, s));
+    return ACB_OK;
+}
+
+static int launch_chain(acb_lm* lm, int ci, cudaStream_t s) {
+    ChainParams cp{};
+    cp.ph = reinterpret_cast<const ChainPhase*>((unsigned char*)lm->buf.plan + ACB_PLAN_COUNTER_BYTES) + lm->chain_off[ci];
+    cp.nph = lm->chain_len[ci]; cp.rows = lm->rows; cp.slab_bytes = lm->chain_slab;
+    cp.bar = reinterpret_cast<unsigned*>(lm->buf.plan) + ci; cp.pos = lm->buf.pos;
+    const dim3 grid(lm->chain_grid), block(128);
+    switch (nt_for_rows(lm->rows)) {   // launched WITHOUT the PDL attribute: all CTAs must become resident at once
+        case 1: ACB_LAUNCH(lm_chain_kernel<1>, grid, block, lm->chain_smem, s, false, cp); break;
+        case 2: ACB_LAUNCH(lm_chain_kernel<2>, grid, block, lm->chain_smem, s, false, cp); break;
+        case 4: ACB_LAUNCH(lm_chain_kernel<4>, grid, block, lm->chain_smem, s, false, cp); break;
+        default: ACB_LAUNCH(lm_chain_kernel<8>, grid, block, lm->chain_smem, s, false, cp); break;
+    }
+    return ACB_OK;
+}
+
 // ACB_DEBUG=1: synchronise and report after every launch of a directly-enqueued step (not during graph capture).
 static bool acb_debug_on() {
     static int v = -1;
@@ -729,8 +1072,8 @@ static int acb_dbg(cudaStream_t s, bool capturing, const char* what, int layer) 
 }
 #define DBG(what, layer) ACB_TRY(acb_dbg(s, capturing, what, layer))
 
-static int enqueue_step(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only = false,
-                        bool capturing = false) {
+static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only,
+                                bool capturing) {
     const acb_lm_config& c = lm->cfg;
     const acb_lm_buffers& B = lm->buf;
     const int d = c.dim, ffn = c.ffn_dim, L = c.num_layers, H = c.num_heads, rows = lm->rows, nt = nt_for_rows(rows);
@@ -837,6 +1180,72 @@ static int enqueue_step(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_la
     return ACB_OK;
 }
 
+// Decode step with chain kernels: embed | chain0 | L x [attn | chainX | cross-attn | chainY] | sample.
+static int enqueue_step_chain(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool chains_only, bool capturing) {
+    const acb_lm_config& c = lm->cfg;
+    const acb_lm_buffers& B = lm->buf;
+    const int d = c.dim, L = c.num_layers, H = c.num_heads, rows = lm->rows;
+    const size_t part_stride = (size_t)lm->rows_pad * d;
+    const size_t kv_layer = (size_t)c.max_rows * H * c.max_seq * 64;
+    const size_t ckv_layer = (size_t)c.max_rows * H * c.max_text * 64;
+    const float scale = 1.0f / sqrtf(64.f);
+    const bool pdl = lm->pdl;
+    int nl = 0, ci = 0;
+    // one barrier counter per chain launch, cleared at the start of the step (a memset node in the graph)
+    ACB_CHECK_CUDA(cudaMemsetAsync(B.plan, 0, lm->chain_off.size() * sizeof(unsigned), s));
+    if (!chains_only) {
+        ACB_LAUNCH(lm_embed_kernel, dim3(rows), dim3(256), 0, s, false, (const __half*)lm->w.emb, lm->w.inv_freq,
+                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale);
+        ++nl;
+        DBG("lm_embed_kernel", -1);
+    }
+    ACB_TRY(launch_chain(lm, ci++, s)); ++nl;
+    DBG("lm_chain_kernel(0)", -1);
+    for (int l = 0; l < L; ++l) {
+        if (!chains_only) {
+            AttnParams a{B.q32, 1, 0, (__half*)B.k_cache + l * kv_layer, (__half*)B.v_cache + l * kv_layer, (__half*)B.a16,
+                         H, d, c.max_seq, B.pos, 0, scale};
+            ACB_LAUNCH(lm_attn_kernel, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            ++nl;
+            DBG("lm_attn_kernel", l);
+        }
+        ACB_TRY(launch_chain(lm, ci++, s)); ++nl;
+        DBG("lm_chain_kernel(X)", l);
+        if (lm->has_cross) {
+            if (!chains_only) {
+                const ChainPhase& cq = lm->plan[lm->chain_off[ci - 1] + lm->chain_len[ci - 1] - 1];   // the CQ GEMM
+                AttnParams a{B.part, cq.nsplit, part_stride, (__half*)B.ck_cache + l * ckv_layer,
+                             (__half*)B.cv_cache + l * ckv_layer, (__half*)B.a16, H, d, c.max_text, B.pos, lm->text_len,
+                             scale};
+                ACB_LAUNCH(lm_cross_attn_kernel, dim3(acb_ceil_div(rows * H, 8)), dim3(256), 0, s, pdl, a, rows);
+                ++nl;
+                DBG("lm_cross_attn_kernel", l);
+            }
+            ACB_TRY(launch_chain(lm, ci++, s)); ++nl;
+            DBG("lm_chain_kernel(Y)", l);
+        }
+    }
+    if (!chains_only) {
+        int NP = 1;
+        while (NP < c.card) NP <<= 1;
+        SampleParams sp{B.logits, lm->samp.noise_from_buffer ? B.noise : nullptr, logits_out, B.seq, B.seq_mask, B.pos,
+                        c.max_seq, nullptr, lm->batch, rows, c.n_q, c.card, NP, lm->samp.use_sampling, lm->samp.top_k,
+                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0};
+        size_t smem = ((size_t)c.card + 2 * (size_t)NP) * sizeof(float);
+        ACB_LAUNCH(lm_sample_kernel, dim3(c.n_q, lm->batch), dim3(1024), smem, s, false, sp);
+        ++nl;
+        DBG("lm_sample_kernel", -1);
+    }
+    if (n_launch) *n_launch = nl;
+    return ACB_OK;
+}
+
+static int enqueue_step(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only = false,
+                        bool capturing = false) {
+    return lm->chain ? enqueue_step_chain(lm, s, logits_out, n_launch, gemms_only, capturing)
+                     : enqueue_step_kernels(lm, s, logits_out, n_launch, gemms_only, capturing);
+}
+
 extern "C" int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, const acb_lm_buffers* buf, acb_lm_t** out) {
     ACB_REQUIRE(cfg && w && buf && out, "acb_lm_create: null argument");
     ACB_REQUIRE(cfg->dim % 64 == 0 && cfg->dim == cfg->num_heads * 64, "acb_lm_create: head_dim must be 64 (dim=%d heads=%d)",
@@ -939,6 +1348,11 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
     {
         const char* e = getenv("ACB_NO_PDL");
         lm->pdl = !(e && e[0] == '1');
+        // persistent chain kernels are an opt-in experiment: measured SLOWER than one kernel per phase on B200
+        // (profiles/r1_perf_step_v5_chain_slower.log, r1_ncu_chain_kernel_raw.csv), see DESIGN.md section 3.1
+        const char* ec = getenv("ACB_LM_CHAIN");
+        lm->chain = (ec && ec[0] == '1') && lm->buf.plan != nullptr;
+        if (lm->chain) ACB_TRY(build_chain_plan(lm, s));
     }
     for (int attempt = 0; attempt < 2; ++attempt) {
         drop_graph(lm);

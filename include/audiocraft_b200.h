@@ -145,9 +145,12 @@ typedef struct {
     uint8_t* seq_mask; /* [n_q][max_seq]     pattern validity mask (codebooks_patterns.py:130-152) */
     int32_t* pos;      /* [4] device ints: pos (tokens in the KV cache), rows, batch, text_len */
     float* noise;      /* [B][n_q][card] Exponential(1) noise, read when sampling.noise_from_buffer != 0 */
+    void* plan;        /* ACB_LM_PLAN_BYTES of scratch: phase lists + grid-barrier counters of the persistent chain
+                          kernels (NULL: every phase is its own kernel) */
 } acb_lm_buffers;
 
 #define ACB_LM_MAX_SPLIT 8
+#define ACB_LM_PLAN_BYTES (2u << 20)
 
 typedef struct {
     int use_sampling;  /* LMModel.generate(use_sampling, temp, top_k, top_p, cfg_coef), lm.py:421-436 */

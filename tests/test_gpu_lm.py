@@ -209,3 +209,20 @@ def test_musicgen_api_shapes_and_callbacks():
     assert tok.shape == (1, 4, int(3.0 * fr))
     with pytest.raises(NotImplementedError):
         mg.generate_with_chroma(['x'], None, 16000)
+
+
+def test_chain_kernel_mode_matches_default(monkeypatch):
+    """ACB_LM_CHAIN=1 (persistent GEMM/LN chain kernels with in-kernel grid barriers) computes the same step as the
+    default one-kernel-per-phase graph; only the split-K partial-sum grouping differs."""
+    cfg, sd, m = _model('lm_mini', 3)
+    B, T = 3, 10
+    _, _, cross = H.lm_condition(cfg, sd, B, 5, 1)
+    seq = torch.randint(0, cfg['card'], (B, 4, T + 4))
+    base = m.teacher_forced_logits(seq, cross, 3.0).cpu()
+    monkeypatch.setenv('ACB_LM_CHAIN', '1')
+    chain = m.teacher_forced_logits(seq, cross, 3.0).cpu()
+    out = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross).cpu()
+    monkeypatch.delenv('ACB_LM_CHAIN')
+    ref = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross).cpu()
+    torch.testing.assert_close(chain, base, rtol=2e-3, atol=2e-3)
+    assert torch.equal(out, ref)
