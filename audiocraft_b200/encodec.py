@@ -340,3 +340,103 @@ class EncodecModel(CompressionModel):
     @staticmethod
     def from_config_name(name: str, state_dict, device='cuda') -> 'EncodecModel':
         return EncodecModel(state_dict, ENCODEC_CONFIGS[name], device)
+
+
+class InterleaveStereoCompressionModel(CompressionModel):
+    """Stereo wrapper over a mono compression model: both channels share the codec and their codebooks are interleaved
+    (`b (k c) t`, or per timestep `b k (t c)`).  Mirror of audiocraft/models/encodec.py:393-506 — same layouts, same
+    properties; the two channels go through the kernels as ONE batch of 2B mono items (items are independent, so this
+    equals the reference's two separate passes)."""
+
+    def __init__(self, model: CompressionModel, per_timestep: bool = False):
+        self.model = model
+        self.per_timestep = per_timestep
+        assert self.model.channels == 1, "Wrapped model is expected to be for monophonic audio"
+
+    @property
+    def total_codebooks(self):
+        return self.model.total_codebooks
+
+    @property
+    def num_codebooks(self):
+        """Active number of codebooks *after* interleaving (encodec.py:420-426)."""
+        return self.model.num_codebooks if self.per_timestep else self.model.num_codebooks * 2
+
+    def set_num_codebooks(self, n: int):
+        """Sets the number of codebooks *before* interleaving (encodec.py:428-433)."""
+        self.model.set_num_codebooks(n)
+
+    @property
+    def num_virtual_steps(self) -> float:
+        return 2 if self.per_timestep else 1
+
+    @property
+    def frame_rate(self) -> float:
+        return self.model.frame_rate * self.num_virtual_steps
+
+    @property
+    def sample_rate(self) -> int:
+        return self.model.sample_rate
+
+    @property
+    def channels(self) -> int:
+        return 2
+
+    @property
+    def cardinality(self):
+        return self.model.cardinality
+
+    def forward(self, x):
+        raise NotImplementedError("Not supported, use encode and decode.")
+
+    def encode(self, x):
+        B, C, T = x.shape
+        assert C == self.channels, f"Expecting stereo audio but audio num channels is {C}"
+        mono = x.transpose(0, 1).reshape(2 * B, 1, T)                       # [c0 items..., c1 items...]
+        indices, scales = self.model.encode(mono)
+        indices = indices.view(2, B, indices.shape[1], indices.shape[2])    # c b k t
+        out_scales = None
+        if scales is not None:
+            out_scales = torch.stack([scales[:B], scales[B:]], dim=1)
+        if self.per_timestep:
+            indices = indices.permute(1, 2, 3, 0).reshape(B, indices.shape[2], -1)          # b k (t c)
+        else:
+            indices = indices.permute(1, 2, 0, 3).reshape(B, -1, indices.shape[3])          # b (k c) t
+        return indices.contiguous(), out_scales
+
+    def get_left_right_codes(self, codes):
+        B = codes.shape[0]
+        if self.per_timestep:
+            c = codes.view(B, codes.shape[1], -1, 2).permute(3, 0, 1, 2)
+        else:
+            c = codes.view(B, -1, 2, codes.shape[2]).permute(2, 0, 1, 3)
+        return c[0].contiguous(), c[1].contiguous()
+
+    def decode(self, codes, scale=None):
+        B, K, T = codes.shape
+        assert T % self.num_virtual_steps == 0, "Provided codes' number of timesteps does not match"
+        assert K == self.num_codebooks, "Provided codes' number of codebooks does not match"
+        scale_c0, scale_c1 = None, None
+        if scale is not None:
+            assert scale.size(0) == B and scale.size(1) == 2, f"Scale has unexpected shape: {scale.shape}"
+            scale_c0 = scale[0, ...]   # as written in the reference (encodec.py:492-493)
+            scale_c1 = scale[1, ...]
+        c0, c1 = self.get_left_right_codes(codes)
+        if scale is None:
+            audio = self.model.decode(torch.cat([c0, c1], dim=0), None)
+            return torch.cat([audio[:B], audio[B:]], dim=1)
+        return torch.cat([self.model.decode(c0, scale_c0), self.model.decode(c1, scale_c1)], dim=1)
+
+    def decode_latent(self, codes):
+        raise NotImplementedError("Not supported by interleaved stereo wrapped models.")
+
+
+def get_wrapped_compression_model(compression_model: CompressionModel, interleave_stereo_codebooks: tp.Optional[dict] = None,
+                                  compression_model_n_q: tp.Optional[int] = None) -> CompressionModel:
+    """audiocraft/models/builders.py:338-351 with the two cfg entries passed explicitly."""
+    if interleave_stereo_codebooks and interleave_stereo_codebooks.get('use'):
+        kwargs = {k: v for k, v in interleave_stereo_codebooks.items() if k != 'use'}
+        compression_model = InterleaveStereoCompressionModel(compression_model, **kwargs)
+    if compression_model_n_q is not None:
+        compression_model.set_num_codebooks(compression_model_n_q)
+    return compression_model

@@ -172,6 +172,25 @@ def golden_sampling():
     print('sampling ok')
 
 
+def golden_stereo():
+    """InterleaveStereoCompressionModel over the tiny mono codec (renormalize off), both interleavings."""
+    enc = R.mod('models.encodec')
+    cfg = dict(synth.ENCODEC_CONFIGS['encodec_tiny'])
+    cfg['renormalize'] = False
+    m = build_ref_encodec(cfg, synth.synth_encodec_state_dict(cfg, seed=1))
+    cfg2 = dict(cfg)
+    cfg2['channels'] = 2
+    x = H.audio_input(cfg2, 2, 900, 9)
+    out = dict(wseed=1, xseed=9, length=900, batch=2)
+    for pt in (False, True):
+        w = enc.InterleaveStereoCompressionModel(m, per_timestep=pt)
+        codes, _ = w.encode(x)
+        out[f'codes_pt{int(pt)}'] = codes
+        out[f'wav_pt{int(pt)}'] = w.decode(codes, None)
+        out[f'props_pt{int(pt)}'] = (w.num_codebooks, w.frame_rate, w.channels, w.cardinality, w.total_codebooks)
+    torch.save(out, os.path.join(H.GOLDEN_DIR, 'encodec_tiny_stereo.pt'))
+
+
 if __name__ == '__main__':
     os.makedirs(H.GOLDEN_DIR, exist_ok=True)
     golden_patterns()
@@ -183,3 +202,4 @@ if __name__ == '__main__':
     golden_lm('lm_mini', 2, 5, 12, 3, 1, steps_logits=15)
     golden_lm('lm_tiny', 3, 4, 9, 4, 2, steps_logits=12)
     golden_lm('musicgen_small', 1, 6, 3, 9, 5, steps_logits=6, topn=32)
+    golden_stereo()

@@ -204,3 +204,27 @@ def test_set_num_codebooks_and_errors():
         m.set_num_codebooks(5)
     with pytest.raises(AssertionError):
         m.encode(torch.zeros(1, 3, 100))
+
+
+def test_interleave_stereo_wrapper_matches_reference_golden():
+    """stereo MusicGen's codec wrapper (audiocraft/models/encodec.py:393-506)."""
+    from audiocraft_b200.encodec import EncodecModel, InterleaveStereoCompressionModel
+    g = torch.load(os.path.join(H.GOLDEN_DIR, 'encodec_tiny_stereo.pt'), weights_only=False)
+    cfg = dict(synth.ENCODEC_CONFIGS['encodec_tiny'])
+    cfg['renormalize'] = False
+    mono = EncodecModel(synth.synth_encodec_state_dict(cfg, seed=g['wseed']), cfg)
+    cfg2 = dict(cfg)
+    cfg2['channels'] = 2
+    x = H.audio_input(cfg2, g['batch'], g['length'], g['xseed'])
+    for pt in (False, True):
+        w = InterleaveStereoCompressionModel(mono, per_timestep=pt)
+        assert (w.num_codebooks, w.frame_rate, w.channels, w.cardinality, w.total_codebooks) == g[f'props_pt{int(pt)}']
+        codes, scale = w.encode(x.cuda())
+        assert scale is None and torch.equal(codes.cpu(), g[f'codes_pt{int(pt)}'])
+        wav = w.decode(g[f'codes_pt{int(pt)}'].cuda())
+        torch.testing.assert_close(wav.cpu(), g[f'wav_pt{int(pt)}'], rtol=0, atol=1e-4)
+        l, r = w.get_left_right_codes(codes)
+        c0, _ = mono.encode(x[:, :1].cuda())
+        assert torch.equal(l, c0)
+    with pytest.raises(AssertionError):
+        InterleaveStereoCompressionModel(mono).encode(x[:, :1].cuda())
