@@ -29,7 +29,8 @@ void acb_set_error(const char* fmt, ...);
 
 static inline int acb_ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-__device__ __forceinline__ float acb_elu(float v) { return v > 0.f ? v : expm1f(v); }
+// ELU(alpha=1) as torch computes it: x > 0 ? x : exp(x) - 1   (ATen elu kernel; not expm1)
+__device__ __forceinline__ float acb_elu(float v) { return v > 0.f ? v : expf(v) - 1.f; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -7,6 +7,7 @@
 // of every activation per layer), weight-norm is folded once at load, the [frames x bins] VQ distance
 // matrix never leaves the SM, and the LSTM keeps W_hh resident in the 227 KB shared memory of 128 SMs.
 #include "common.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
 // weight-norm fold: w[g][:] = g[g] * v[g][:] / ||v[g]||   (audiocraft/modules/conv.py:21-30)
@@ -86,10 +87,18 @@ __global__ void __launch_bounds__(256) conv1d_kernel(ConvParams p) {
             int r = idx / BM, c = idx - r * BM;
             ws[idx] = (co0 + c < p.c_out) ? p.w[((size_t)ci0 * p.K + r) * p.c_out + co0 + c] : 0.f;
         }
-        for (int idx = tid; idx < nci * p.span; idx += 256) {
-            int cl = idx / p.span, j = idx - cl * p.span;
-            float v = conv_fetch(xb + (size_t)(ci0 + cl) * p.t_in, g0 + j, p.t_in, p.t_virt, p.reflect, p.elu);
-            xs[cl * XS + (j % p.stride) * p.PL + j / p.stride] = v;
+        // one warp per staged input channel: no integer division in the index math
+        for (int cl = warp; cl < nci; cl += 8) {
+            const float* xrow = xb + (size_t)(ci0 + cl) * p.t_in;
+            float* xdst = xs + cl * XS;
+            if (p.stride == 1) {
+                for (int j = lane; j < p.span; j += 32)
+                    xdst[j] = conv_fetch(xrow, g0 + j, p.t_in, p.t_virt, p.reflect, p.elu);
+            } else {
+                for (int ph = 0; ph < p.stride; ++ph)
+                    for (int q = lane; q * p.stride + ph < p.span; q += 32)
+                        xdst[ph * p.PL + q] = conv_fetch(xrow, g0 + q * p.stride + ph, p.t_in, p.t_virt, p.reflect, p.elu);
+            }
         }
         __syncthreads();
         for (int cl = 0; cl < nci; ++cl) {
@@ -127,9 +136,9 @@ __global__ void __launch_bounds__(256) conv1d_kernel(ConvParams p) {
     }
 }
 
-template <int CPT>
+template <int CPT, int TPT>
 static int launch_conv1d(const ConvParams& p, int batch, cudaStream_t s) {
-    constexpr int TPT = 4, BM = 8 * CPT, BN = 32 * TPT;
+    constexpr int BM = 8 * CPT, BN = 32 * TPT;
     ConvParams q = p;
     q.ci_chunk = max(1, min(p.c_in, 32 / p.K));
     q.span = (BN - 1) * p.stride + (p.K - 1) * p.dil + 1;
@@ -146,9 +155,235 @@ static int launch_conv1d(const ConvParams& p, int batch, cudaStream_t s) {
     return ACB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// conv1d on the tensor pipe with fp32-level accuracy: 3xTF32.  Every fp32 operand is split into hi = tf32(x) and
+// lo = tf32(x - hi); acc += hi*hi + hi*lo + lo*hi (the lo*lo term, 2^-22 relative, is dropped), fp32 accumulate.
+// The 3-register FFMA path tops out near 37 TFLOP/s on this part; the tensor pipe does the same implicit GEMM several
+// times faster while keeping the latents within ~1e-6 of the fp32 reference (RVQ indices stay put).
+// CTA tile 64 output channels x 128 steps, 8 warps as 2 (channels) x 4 (time), warp tile 32 x 32 = 2 x 4 m16n8k8 tiles.
+// B fragments are read straight from the staged (padded, ELU'd, phase-de-interleaved) input slab through a per-chunk
+// row-offset table, i.e. the im2col matrix is never materialised.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int TC_BM = 64, TC_BN = 128, TC_WP = TC_BM + 8;   // W smem row pitch = 8 mod 32: conflict-free A fragments
+
+__global__ void __launch_bounds__(256) conv1d_tc_kernel(ConvParams p, int xsp, int rcp) {
+    extern __shared__ float smem[];
+    float* wh = smem;                          // [rcp][TC_WP] tf32 hi
+    float* wl = wh + rcp * TC_WP;              // [rcp][TC_WP] tf32 lo
+    float* xs = wl + rcp * TC_WP;              // [ci_chunk][xsp]
+    int* roff = (int*)(xs + p.ci_chunk * xsp); // [rcp] slab offset of reduction row r = (channel, tap)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+    const int wm = warp & 1, wn = warp >> 1;
+    const int t0 = blockIdx.x * TC_BN, co0 = blockIdx.y * TC_BM, b = blockIdx.z;
+    const float* xb = p.x + (size_t)b * p.c_in * p.t_in;
+
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+
+    const int g0 = t0 * p.stride - p.pad_left;
+    for (int ci0 = 0; ci0 < p.c_in; ci0 += p.ci_chunk) {
+        const int nci = min(p.ci_chunk, p.c_in - ci0);
+        const int rc = nci * p.K, rcu = (rc + 7) & ~7;
+        __syncthreads();
+        for (int idx = tid; idx < rcu * TC_BM; idx += 256) {
+            const int r = idx / TC_BM, cc = idx - r * TC_BM;
+            const float w = (r < rc && co0 + cc < p.c_out) ? p.w[((size_t)ci0 * p.K + r) * p.c_out + co0 + cc] : 0.f;
+            const uint32_t hi = to_tf32(w);
+            wh[r * TC_WP + cc] = __uint_as_float(hi);
+            wl[r * TC_WP + cc] = __uint_as_float(to_tf32(w - __uint_as_float(hi)));
+        }
+        for (int r = tid; r < rcu; r += 256) {
+            int off = 0;
+            if (r < rc) {
+                const int cl = r / p.K, k = r - cl * p.K, kd = k * p.dil;
+                off = cl * xsp + (kd % p.stride) * p.PL + kd / p.stride;
+            }
+            roff[r] = off;
+        }
+        for (int cl = warp; cl < nci; cl += 8) {
+            const float* xrow = xb + (size_t)(ci0 + cl) * p.t_in;
+            float* xdst = xs + cl * xsp;
+            if (p.stride == 1) {
+                for (int j = lane; j < p.span; j += 32)
+                    xdst[j] = conv_fetch(xrow, g0 + j, p.t_in, p.t_virt, p.reflect, p.elu);
+            } else {
+                for (int ph = 0; ph < p.stride; ++ph)
+                    for (int q = lane; q * p.stride + ph < p.span; q += 32)
+                        xdst[ph * p.PL + q] = conv_fetch(xrow, g0 + q * p.stride + ph, p.t_in, p.t_virt, p.reflect, p.elu);
+            }
+        }
+        __syncthreads();
+        const float* xw = xs + wn * 32 + g;
+        for (int kk = 0; kk < rcu; kk += 8) {
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int m = wm * 32 + mt * 16 + g;
+                ah[mt][0] = __float_as_uint(wh[(kk + c) * TC_WP + m]);
+                ah[mt][1] = __float_as_uint(wh[(kk + c) * TC_WP + m + 8]);
+                ah[mt][2] = __float_as_uint(wh[(kk + c + 4) * TC_WP + m]);
+                ah[mt][3] = __float_as_uint(wh[(kk + c + 4) * TC_WP + m + 8]);
+                al[mt][0] = __float_as_uint(wl[(kk + c) * TC_WP + m]);
+                al[mt][1] = __float_as_uint(wl[(kk + c) * TC_WP + m + 8]);
+                al[mt][2] = __float_as_uint(wl[(kk + c + 4) * TC_WP + m]);
+                al[mt][3] = __float_as_uint(wl[(kk + c + 4) * TC_WP + m + 8]);
+            }
+            const int o0 = roff[kk + c], o1 = roff[kk + c + 4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float x0 = xw[o0 + nt * 8], x1 = xw[o1 + nt * 8];
+                const uint32_t bh0 = to_tf32(x0), bh1 = to_tf32(x1);
+                const uint32_t bl0 = to_tf32(x0 - __uint_as_float(bh0)), bl1 = to_tf32(x1 - __uint_as_float(bh1));
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_tf32(acc[mt][nt], al[mt], bh0, bh1);
+                    mma_tf32(acc[mt][nt], ah[mt], bl0, bl1);
+                    mma_tf32(acc[mt][nt], ah[mt], bh0, bh1);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int co = co0 + wm * 32 + mt * 16 + g + 8 * hrow;
+            if (co >= p.c_out) continue;
+            const float bv = p.bias ? p.bias[co] : 0.f;
+            const size_t row = ((size_t)b * p.c_out + co) * p.t_out;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int t = t0 + wn * 32 + nt * 8 + 2 * c + e;
+                    if (t < p.t_out) {
+                        float v = acc[mt][nt][2 * hrow + e] + bv;
+                        if (p.res) v += p.res[row + t];
+                        p.y[row + t] = v;
+                    }
+                }
+        }
+}
+
+static int launch_conv1d_tc(const ConvParams& p, int batch, cudaStream_t s) {
+    ConvParams q = p;
+    q.ci_chunk = max(1, min(p.c_in, 32 / p.K));
+    q.span = (TC_BN - 1) * p.stride + (p.K - 1) * p.dil + 1;
+    q.PL = acb_ceil_div(q.span, p.stride);
+    int xsp = p.stride * q.PL;
+    xsp += (8 - (xsp & 31) + 32) & 31;            // channel pitch = 8 mod 32: conflict-free B fragments
+    const int rcp = (q.ci_chunk * p.K + 7) & ~7;
+    size_t smem = ((size_t)2 * rcp * TC_WP + (size_t)q.ci_chunk * xsp) * sizeof(float) + rcp * sizeof(int);
+    ACB_REQUIRE(smem <= 200 * 1024, "acb_conv1d: tensor-core tile needs %zu B of shared memory", smem);
+    if (smem > 48 * 1024)
+        ACB_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(acb_ceil_div(p.t_out, TC_BN), acb_ceil_div(p.c_out, TC_BM), batch);
+    conv1d_tc_kernel<<<grid, 256, smem, s>>>(q, xsp, rcp);
+    ACB_LAUNCH_CHECK();
+    return ACB_OK;
+}
+
+// Few output channels (the decoder's last conv, Cout = audio channels): a thread owns 4 consecutive output steps of
+// every output channel and slides a register window over the taps, so the kernel is a pure stream over x.
+constexpr int SC_MAXCO = 4, SC_TILE = 1024;
+struct SmallCoParams {
+    const float* x; const float* w; const float* bias; const float* res; float* y;
+    int c_in, c_out, t_in, t_virt, t_out, K, pad_left, reflect, elu, ci_chunk;
+};
+template <int KT>
+__global__ void __launch_bounds__(256) conv1d_small_cout_kernel(SmallCoParams p) {
+    extern __shared__ float smem[];
+    constexpr int span = SC_TILE + KT - 1;
+    constexpr int pitch = SC_TILE + 12;            // row pitch: multiple of 4 floats so the window loads are LDS.128
+    static_assert(KT + 3 <= 12, "window of 3 float4");
+    float* xs = smem;                              // [ci_chunk][pitch]
+    float* ws = xs + p.ci_chunk * pitch;           // [ci_chunk][KT][SC_MAXCO]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * SC_TILE, b = blockIdx.y;
+    const float* xb = p.x + (size_t)b * p.c_in * p.t_in;
+    float acc[SC_MAXCO][4];
+#pragma unroll
+    for (int c = 0; c < SC_MAXCO; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    const int g0 = t0 - p.pad_left;
+    for (int ci0 = 0; ci0 < p.c_in; ci0 += p.ci_chunk) {
+        const int nci = min(p.ci_chunk, p.c_in - ci0);
+        __syncthreads();
+        for (int cl = warp; cl < nci; cl += 8) {
+            const float* xrow = xb + (size_t)(ci0 + cl) * p.t_in;
+            for (int j = lane; j < pitch; j += 32)
+                xs[cl * pitch + j] = j < span ? conv_fetch(xrow, g0 + j, p.t_in, p.t_virt, p.reflect, p.elu) : 0.f;
+        }
+        for (int idx = tid; idx < nci * KT * SC_MAXCO; idx += 256) {
+            const int c = idx % SC_MAXCO, rk = idx / SC_MAXCO;   // rk = cl*KT + k
+            ws[idx] = c < p.c_out ? p.w[((size_t)ci0 * KT + rk) * p.c_out + c] : 0.f;
+        }
+        __syncthreads();
+        for (int cl = 0; cl < nci; ++cl) {
+            float xw[12];
+            const float4* xr4 = reinterpret_cast<const float4*>(xs + cl * pitch + tid * 4);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float4 v4 = xr4[i];
+                xw[4 * i] = v4.x; xw[4 * i + 1] = v4.y; xw[4 * i + 2] = v4.z; xw[4 * i + 3] = v4.w;
+            }
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                const float4 wv = *reinterpret_cast<const float4*>(ws + (cl * KT + k) * SC_MAXCO);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[0][j] = fmaf(wv.x, xw[k + j], acc[0][j]);
+                    acc[1][j] = fmaf(wv.y, xw[k + j], acc[1][j]);
+                    acc[2][j] = fmaf(wv.z, xw[k + j], acc[2][j]);
+                    acc[3][j] = fmaf(wv.w, xw[k + j], acc[3][j]);
+                }
+            }
+        }
+    }
+    for (int c = 0; c < p.c_out; ++c) {
+        const float bv = p.bias ? p.bias[c] : 0.f;
+        const size_t row = ((size_t)b * p.c_out + c) * p.t_out;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t = t0 + tid * 4 + j;
+            if (t < p.t_out) {
+                float v = (c == 0 ? acc[0][j] : c == 1 ? acc[1][j] : c == 2 ? acc[2][j] : acc[3][j]) + bv;
+                if (p.res) v += p.res[row + t];
+                p.y[row + t] = v;
+            }
+        }
+    }
+}
+
+template <int KT>
+static int launch_small_cout(const SmallCoParams& p, int batch, cudaStream_t s) {
+    SmallCoParams q = p;
+    q.ci_chunk = min(p.c_in, 8);
+    size_t smem = ((size_t)q.ci_chunk * (SC_TILE + 12) + (size_t)q.ci_chunk * KT * SC_MAXCO) * sizeof(float);
+    dim3 grid(acb_ceil_div(p.t_out, SC_TILE), batch);
+    conv1d_small_cout_kernel<KT><<<grid, 256, smem, s>>>(q);
+    ACB_LAUNCH_CHECK();
+    return ACB_OK;
+}
+
 extern "C" int acb_conv1d(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
                           int batch, int c_in, int c_out, int t_in, int t_virtual, int t_out, int kernel, int stride,
-                          int dilation, int pad_left, int reflect, int elu_in, void* stream) {
+                          int dilation, int pad_left, int reflect, int elu_in, int precision, void* stream) {
     ACB_REQUIRE(x && w_packed && y, "acb_conv1d: null pointer");
     ACB_REQUIRE(batch > 0 && c_in > 0 && c_out > 0 && t_in > 0 && t_out > 0, "acb_conv1d: empty shape");
     ACB_REQUIRE(kernel >= 1 && kernel <= 64 && stride >= 1 && dilation >= 1 && pad_left >= 0, "acb_conv1d: bad taps");
@@ -157,10 +392,18 @@ extern "C" int acb_conv1d(const float* x, const float* w_packed, const float* bi
     ConvParams p{x, w_packed, bias, residual, y, c_in, c_out, t_in, t_virtual, t_out, kernel, stride, dilation,
                  pad_left, reflect, elu_in, 0, 0, 0};
     cudaStream_t s = (cudaStream_t)stream;
-    if (c_out >= 64) return launch_conv1d<8>(p, batch, s);
-    if (c_out >= 32) return launch_conv1d<4>(p, batch, s);
-    if (c_out >= 16) return launch_conv1d<2>(p, batch, s);
-    return launch_conv1d<1>(p, batch, s);
+    if (c_out <= SC_MAXCO && stride == 1 && dilation == 1 && (kernel == 7 || kernel == 3)) {
+        SmallCoParams q{x, w_packed, bias, residual, y, c_in, c_out, t_in, t_virtual, t_out, kernel, pad_left, reflect, elu_in, 0};
+        return kernel == 7 ? launch_small_cout<7>(q, batch, s) : launch_small_cout<3>(q, batch, s);
+    }
+    ACB_REQUIRE(precision == ACB_CONV_FP32 || precision == ACB_CONV_TF32X3, "acb_conv1d: unknown precision %d", precision);
+    // tensor pipe (3xTF32) when asked for and the layer has enough channels / reduction depth to fill the MMA tiles
+    if (precision == ACB_CONV_TF32X3 && c_out >= 32 && c_in * kernel >= 16) return launch_conv1d_tc(p, batch, s);
+    const bool wide = t_out >= 2048;   // 8 output steps per thread once there is enough time axis to fill the tile
+    if (c_out >= 64) return wide ? launch_conv1d<8, 8>(p, batch, s) : launch_conv1d<8, 4>(p, batch, s);
+    if (c_out >= 32) return wide ? launch_conv1d<4, 8>(p, batch, s) : launch_conv1d<4, 4>(p, batch, s);
+    if (c_out >= 16) return launch_conv1d<2, 4>(p, batch, s);
+    return launch_conv1d<1, 4>(p, batch, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -284,7 +527,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 
-constexpr int LSTM_BC = 8;  // batch items per matvec pass
+constexpr int LSTM_BC = 16;  // batch items per matvec pass
 
 __global__ void __launch_bounds__(256) lstm_kernel(LstmParams p) {
     extern __shared__ float smem[];
@@ -330,39 +573,43 @@ __global__ void __launch_bounds__(256) lstm_kernel(LstmParams p) {
                 }
                 __syncthreads();
                 for (int r0 = warp * 4; r0 < R; r0 += 32) {
-                    float acc[32];
+                    float acc[4 * LSTM_BC];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                    for (int i = 0; i < 4 * LSTM_BC; ++i) acc[i] = 0.f;
                     for (int kk = lane * 4; kk < H; kk += 128) {
-                        float4 w4[4], h4[LSTM_BC];
+                        float4 w4[4];
 #pragma unroll
                         for (int r = 0; r < 4; ++r) w4[r] = *reinterpret_cast<const float4*>(wsm + (size_t)(r0 + r) * H + kk);
 #pragma unroll
-                        for (int bb = 0; bb < LSTM_BC; ++bb) h4[bb] = *reinterpret_cast<const float4*>(hs + (size_t)bb * H + kk);
+                        for (int bb = 0; bb < LSTM_BC; ++bb) {
+                            const float4 h4 = *reinterpret_cast<const float4*>(hs + (size_t)bb * H + kk);
 #pragma unroll
-                        for (int r = 0; r < 4; ++r)
-#pragma unroll
-                            for (int bb = 0; bb < LSTM_BC; ++bb) {
+                            for (int r = 0; r < 4; ++r) {
                                 float a = acc[r * LSTM_BC + bb];
-                                a = fmaf(w4[r].x, h4[bb].x, a);
-                                a = fmaf(w4[r].y, h4[bb].y, a);
-                                a = fmaf(w4[r].z, h4[bb].z, a);
-                                a = fmaf(w4[r].w, h4[bb].w, a);
+                                a = fmaf(w4[r].x, h4.x, a);
+                                a = fmaf(w4[r].y, h4.y, a);
+                                a = fmaf(w4[r].z, h4.z, a);
+                                a = fmaf(w4[r].w, h4.w, a);
                                 acc[r * LSTM_BC + bb] = a;
                             }
-                    }
-                    // transpose-reduce: afterwards lane l holds the warp-wide sum of acc[l]
-#pragma unroll
-                    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-                        const bool upper = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < n; ++i) {
-                            float send = upper ? acc[i] : acc[i + n];
-                            float keep = upper ? acc[i + n] : acc[i];
-                            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                         }
                     }
-                    gs[(r0 + lane / LSTM_BC) * LSTM_BC + (lane % LSTM_BC)] = acc[0];
+                    // transpose-reduce 32 values at a time: afterwards lane l holds the warp-wide sum of acc[half*32 + l]
+#pragma unroll
+                    for (int half = 0; half < (4 * LSTM_BC) / 32; ++half) {
+#pragma unroll
+                        for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+                            const bool upper = (lane & off) != 0;
+#pragma unroll
+                            for (int i = 0; i < n; ++i) {
+                                float send = upper ? acc[half * 32 + i] : acc[half * 32 + i + n];
+                                float keep = upper ? acc[half * 32 + i + n] : acc[half * 32 + i];
+                                acc[half * 32 + i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            }
+                        }
+                        const int vi = half * 32 + lane;   // value index = r * LSTM_BC + bb
+                        gs[(r0 + vi / LSTM_BC) * LSTM_BC + (vi % LSTM_BC)] = acc[half * 32];
+                    }
                 }
                 __syncthreads();
             }

@@ -119,8 +119,14 @@ def convtr_geometry(length: int, kernel: int, stride: int, causal: bool, trim_ri
 class EncodecModel(CompressionModel):
     """EnCodec (SEANet + RVQ) on B200 behind the reference's ``EncodecModel`` API."""
 
-    def __init__(self, state_dict: tp.Dict[str, torch.Tensor], cfg: dict, device='cuda'):
+    def __init__(self, state_dict: tp.Dict[str, torch.Tensor], cfg: dict, device='cuda',
+                 encoder_precision: str = 'fp32', decoder_precision: str = 'tf32x3'):
+        """encoder_precision / decoder_precision: 'fp32' (FMA) or 'tf32x3' (tensor pipe, split operands).  The encoder
+        defaults to fp32 so that RVQ indices equal the fp32 reference's; the decoder's output is a waveform checked to a
+        tolerance (1e-4) and defaults to the faster 3xTF32 convolutions."""
         self.device = _lib.require_cuda(device)
+        prec = {'fp32': _lib.CONV_FP32, 'tf32x3': _lib.CONV_TF32X3}
+        self._enc_prec, self._dec_prec = prec[encoder_precision], prec[decoder_precision]
         self._lib = _lib.lib()
         self.cfg = dict(cfg)
         self._channels = cfg['channels']
@@ -180,7 +186,8 @@ class EncodecModel(CompressionModel):
         return out
 
     # ------------------------------------------------------------------ layer launches
-    def _conv(self, x, L, w=None, b=None, res=None, k=None, stride=None, dilation=None, elu=None, cout=None):
+    def _conv(self, x, L, w=None, b=None, res=None, k=None, stride=None, dilation=None, elu=None, cout=None,
+              prec=0):
         B, cin, T = x.shape
         k = L['k'] if k is None else k
         stride = L['stride'] if stride is None else stride
@@ -191,7 +198,7 @@ class EncodecModel(CompressionModel):
         _lib.check(self._lib.acb_conv1d(_lib.ptr(x), _lib.ptr(L['w'] if w is None else w),
                                         _lib.ptr(L['b'] if b is None else b), _lib.ptr(res), _lib.ptr(y),
                                         B, cin, cout, T, t_virt, t_out, k, stride, dilation, left, self.reflect,
-                                        int(L['elu'] if elu is None else elu), _lib.stream()), 'conv1d')
+                                        int(L['elu'] if elu is None else elu), prec, _lib.stream()), 'conv1d')
         self.launches += 1
         return y
 
@@ -205,7 +212,7 @@ class EncodecModel(CompressionModel):
         self.launches += 1
         return y
 
-    def _lstm(self, x, L):
+    def _lstm(self, x, L, prec=0):
         """y = LSTM(x) + x over frames (audiocraft/modules/lstm.py:19-25): per layer one 1x1 conv for the input
         half of the gates, then the persistent recurrent kernel."""
         B, H, T = x.shape
@@ -215,7 +222,7 @@ class EncodecModel(CompressionModel):
         for n in range(n_layers):
             gx = torch.empty((B, 4 * H, T), device=x.device, dtype=torch.float32)
             _lib.check(self._lib.acb_conv1d(_lib.ptr(inp), _lib.ptr(L['w_ih'][n]), _lib.ptr(L['bias'][n]), None,
-                                            _lib.ptr(gx), B, H, 4 * H, T, T, T, 1, 1, 1, 0, 0, 0, _lib.stream()),
+                                            _lib.ptr(gx), B, H, 4 * H, T, T, T, 1, 1, 1, 0, 0, 0, prec, _lib.stream()),
                        'lstm input conv')
             y = torch.empty((B, H, T), device=x.device, dtype=torch.float32)
             skip = x if n == n_layers - 1 else None
@@ -225,18 +232,26 @@ class EncodecModel(CompressionModel):
             inp = y
         return inp
 
-    def _run(self, x, layers):
+    def _run(self, x, layers, prec=0):
         skip = None
+        prof = getattr(self, '_profile', None)   # optional per-layer CUDA-event timing (profiles/perf_encodec.py)
         for L in layers:
+            if prof is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                shape_in = tuple(x.shape)
             if L['kind'] == 'conv':
                 if L['res'] == 'in':
                     skip = x
                 res = skip if L['res'] == 'out' else None
-                x = self._conv(x, L, res=res)
+                x = self._conv(x, L, res=res, prec=prec)
             elif L['kind'] == 'convtr':
                 x = self._convtr(x, L)
             else:
-                x = self._lstm(x, L)
+                x = self._lstm(x, L, prec=prec)
+            if prof is not None:
+                e1.record()
+                prof.append((L, shape_in, tuple(x.shape), e0, e1))
         return x
 
     # ------------------------------------------------------------------ reference API
@@ -291,7 +306,7 @@ class EncodecModel(CompressionModel):
     def encode_latent(self, x):
         """SEANetEncoder.forward (audiocraft/modules/seanet.py:152-153) on pre-processed input."""
         with torch.cuda.device(self.device):
-            return self._run(self._in(x), self.enc)
+            return self._run(self._in(x), self.enc, self._enc_prec)
 
     def quantize(self, emb):
         """ResidualVectorQuantizer.encode (vq.py:87-96): latent [B,D,T] -> codes [B,n_q,T] int64."""
@@ -307,7 +322,7 @@ class EncodecModel(CompressionModel):
         """encodec.py:223-238."""
         with torch.cuda.device(self.device):
             x, scale = self.preprocess(self._in(x))
-            emb = self._run(x.contiguous(), self.enc)
+            emb = self._run(x.contiguous(), self.enc, self._enc_prec)
             return self.quantize(emb), scale
 
     def decode_latent(self, codes):
@@ -326,7 +341,7 @@ class EncodecModel(CompressionModel):
     def decode(self, codes, scale=None):
         """encodec.py:240-255; like the reference the output keeps the decoder's extra padding."""
         with torch.cuda.device(self.device):
-            out = self._run(self.decode_latent(codes), self.dec)
+            out = self._run(self.decode_latent(codes), self.dec, self._dec_prec)
             return self.postprocess(out, scale)
 
     def forward(self, x):

@@ -95,7 +95,10 @@ def dist_setup(n):
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     if torch.cuda.is_available():
         torch.cuda.set_device(local)
-    dist.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
+    if torch.cuda.is_available():
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        dist.init_process_group('gloo')
     return rank, world
 
 
@@ -203,10 +206,16 @@ def run_b200(args):
     torch.cuda.synchronize()
     gemm_ms = e0.elapsed_time(e1) / reps
     pk = peaks()
+    traffic = None   # dram__bytes_read+write of lm_gemm_kernel over one step, from the committed ncu capture
+    tp = os.path.join(ROOT, 'profiles', 'r1_step_kv750_v3_dram_summary.json')
+    if os.path.exists(tp) and args.scale == 'medium' and B == 8:
+        tj = json.load(open(tp)).get('lm_gemm_kernel')
+        if tj:
+            traffic = int((tj['dram_read_MB'] + tj['dram_write_MB']) * 1e6)
     achieved = w_step / (gemm_ms / 1e3) / 1e9
     step_ms = ms / args.steps / (S - 1)  # includes the EnCodec decode, amortised
     roofline = dict(bound='hbm', kernel='lm_gemm_kernel', achieved=round(achieved, 1), peak=pk['hbm_gbs'], unit='GB/s',
-                    frac=round(achieved / pk['hbm_gbs'], 4), traffic=None, peak_source=pk['source'],
+                    frac=round(achieved / pk['hbm_gbs'], 4), traffic=traffic, peak_source=pk['source'],
                     launches_per_pass=nl.value, bytes_per_pass=w_step, ms_per_pass=round(gemm_ms, 4),
                     whole_generate=dict(algorithmic_bytes=total_bytes, achieved=round(total_bytes / (ms / args.steps / 1e3) / 1e9, 1),
                                         frac=round(total_bytes / (ms / args.steps / 1e3) / 1e9 / pk['hbm_gbs'], 4),
@@ -228,7 +237,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         enc_ms = e0.elapsed_time(e1) / 3
         secondary = dict(metric='EnCodec 32kHz encode+decode MSamples/sec', value=round(xb.numel() / (enc_ms / 1e3) / 1e6, 2),
-                         unit='MSamples/s', config='32 x 10 s mono per GPU, fp32', ms=round(enc_ms, 2))
+                         unit='MSamples/s', config='32 x 10 s mono per GPU; encoder fp32 FMA, decoder 3xTF32 tensor pipe', ms=round(enc_ms, 2))
 
     cpu_baseline = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu:

@@ -58,7 +58,12 @@ int acb_weight_norm_fold(const float* v, const float* g, float* w, int groups, i
  * w_packed is [Cin*K][Cout] (tap-major, Cout contiguous), folded fp32 weights. */
 int acb_conv1d(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
                int batch, int c_in, int c_out, int t_in, int t_virtual, int t_out, int kernel, int stride,
-               int dilation, int pad_left, int reflect, int elu_in, void* stream);
+               int dilation, int pad_left, int reflect, int elu_in, int precision, void* stream);
+/* precision: ACB_CONV_FP32 = fp32 FMA (what the RVQ-exact encoder uses); ACB_CONV_TF32X3 = tensor pipe with every fp32
+ * operand split into two tf32 terms and three MMAs per product (~2^-22 relative error per product, fp32 accumulate) --
+ * layers too small for the MMA tile fall back to fp32 FMA. */
+#define ACB_CONV_FP32 0
+#define ACB_CONV_TF32X3 1
 
 /* StreamableConvTranspose1d.forward, audiocraft/modules/conv.py:221-243: transposed conv (kernel = 2*stride)
  * followed by the fixed trim, computed directly in trimmed coordinates:

@@ -36,7 +36,7 @@ def test_conv1d_matches_oracle(cin, cout, k, s, d, causal, L):
     x = torch.randn(2, cin, L, generator=g)
     w = torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5
     b = torch.randn(cout, generator=g)
-    for elu, with_res in [(False, False), (True, True)]:
+    for elu, with_res, prec in [(False, False, 0), (True, True, 0), (True, True, 1), (False, False, 1)]:
         ref = EO.sconv1d(EO.elu(x) if elu else x, w, b, stride=s, dilation=d, causal=causal)
         res = torch.randn(ref.shape, generator=g) if with_res else None
         if with_res:
@@ -47,7 +47,8 @@ def test_conv1d_matches_oracle(cin, cout, k, s, d, causal, L):
         rd = _dev(res) if with_res else None
         y = torch.empty(2, cout, tout, device='cuda')
         lib.check(L_.acb_conv1d(lib.ptr(xd), lib.ptr(wd), lib.ptr(bd), lib.ptr(rd), lib.ptr(y), 2, cin, cout, L, tv, tout,
-                                k, s, d, left, 1, int(elu), lib.stream()))
+                                k, s, d, left, 1, int(elu), prec, lib.stream()))
+        # prec 1 = 3xTF32 on the tensor pipe (fp32 FMA fallback for tiny layers): same tolerance, one layer deep
         torch.testing.assert_close(y.cpu(), ref, rtol=1e-4, atol=1e-4)
 
 
@@ -143,7 +144,7 @@ def test_encodec_model_matches_reference_golden(name):
     cfg = synth.ENCODEC_CONFIGS[name]
     sd = synth.synth_encodec_state_dict(cfg, seed=g['wseed'])
     x = H.audio_input(cfg, g['batch'], g['length'], g['xseed'])
-    m = EncodecModel(sd, cfg)
+    m = EncodecModel(sd, cfg)   # defaults: fp32 encoder (index-exact), 3xTF32 decoder
     lat = m.encode_latent(m.preprocess(x.cuda())[0])
     torch.testing.assert_close(lat.cpu(), g['latent'], rtol=0, atol=1e-4)
     codes, scale = m.encode(x)
@@ -153,13 +154,17 @@ def test_encodec_model_matches_reference_golden(name):
     _codes_match(codes.cpu(), g['codes'], margins, name)
     if g['scale'] is not None:
         torch.testing.assert_close(scale.cpu(), g['scale'], rtol=1e-5, atol=0)
-    wav = m.decode(g['codes'].cuda(), None if g['scale'] is None else g['scale'].cuda()).cpu()
-    if 'wav' in g:
-        torch.testing.assert_close(wav, g['wav'], rtol=0, atol=1e-4)
-    else:
-        assert wav.shape[-1] == g['wav_len']
-        torch.testing.assert_close(wav[..., :512], g['wav_head'], rtol=0, atol=1e-4)
-        torch.testing.assert_close(wav[..., ::g['wav_stride']], g['wav_strided'], rtol=0, atol=1e-4)
+    sc = None if g['scale'] is None else g['scale'].cuda()
+    for mdl, tol in ((m, 1e-4), (EncodecModel(sd, cfg, decoder_precision='fp32'), 2e-5)):
+        wav = mdl.decode(g['codes'].cuda(), sc).cpu()
+        if 'wav' in g:
+            print(f'{name} decoder max err {(wav - g["wav"]).abs().max():.2e} (tol {tol})')
+            torch.testing.assert_close(wav, g['wav'], rtol=0, atol=tol)
+        else:
+            assert wav.shape[-1] == g['wav_len']
+            print(f'{name} decoder max err {(wav[..., ::g["wav_stride"]] - g["wav_strided"]).abs().max():.2e} (tol {tol})')
+            torch.testing.assert_close(wav[..., :512], g['wav_head'], rtol=0, atol=tol)
+            torch.testing.assert_close(wav[..., ::g['wav_stride']], g['wav_strided'], rtol=0, atol=tol)
 
 
 def test_encodec_32k_properties_at_size():
