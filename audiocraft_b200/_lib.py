@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libaudiocraft_b200.so')
 
-CONV_FP32, CONV_TF32X3 = 0, 1
+CONV_FP32, CONV_TF32X3, CONV_TF32X3_MMASYNC = 0, 1, 2
 ACB_LM_MAX_SPLIT = 8
 ACB_LM_PLAN_BYTES = 2 << 20
 
@@ -55,7 +55,7 @@ def lib():
     L.acb_device_sm_count.argtypes = [ci]
     L.acb_weight_norm_fold.argtypes = [vp, vp, vp, ci, ci, vp]
     L.acb_conv1d.argtypes = [vp, vp, vp, vp, vp] + [ci] * 13 + [vp]
-    L.acb_convtr1d.argtypes = [vp, vp, vp, vp] + [ci] * 9 + [vp]
+    L.acb_convtr1d.argtypes = [vp, vp, vp, vp, vp] + [ci] * 10 + [vp]
     L.acb_lstm_recurrent.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
     L.acb_lstm_state_bytes.argtypes = [ci, ci]
     L.acb_lstm_state_bytes.restype = i64

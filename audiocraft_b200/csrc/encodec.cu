@@ -43,6 +43,7 @@ extern "C" int acb_weight_norm_fold(const float* v, const float* g, float* w, in
 struct ConvParams {
     const float* x; const float* w; const float* bias; const float* res; float* y;
     int c_in, c_out, t_in, t_virt, t_out, K, stride, dil, pad_left, reflect, elu, ci_chunk, span, PL;
+    int tr_S, tr_trim, tr_tout;   // transposed conv as a GEMM over virtual channels n' = co*S + phase (tcgen05 kernel only)
 };
 
 __device__ __forceinline__ float conv_fetch(const float* __restrict__ xr, int g, int t_in, int t_virt, int reflect,
@@ -164,6 +165,7 @@ static int launch_conv1d(const ConvParams& p, int batch, cudaStream_t s) {
 // B fragments are read straight from the staged (padded, ELU'd, phase-de-interleaved) input slab through a per-chunk
 // row-offset table, i.e. the im2col matrix is never materialised.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32_(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -299,6 +301,199 @@ static int launch_conv1d_tc(const ConvParams& p, int batch, cudaStream_t s) {
     return ACB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// conv1d on the 5th-generation tensor cores: tcgen05.mma.kind::tf32 with the accumulator in TMEM, 3xTF32 split.
+//   D[128 time steps (TMEM lanes)][N output channels (TMEM columns)] += A[128][8] . B[N][8]^T   per instruction
+//   A = im2col rows of the staged input slab, B = weight rows, both K-major in the canonical no-swizzle layout
+//       offset(row, k16B) = k16B * LBO + (row / 8) * 128 B + (row % 8) * 16 B      (8x16B core matrices, SBO = 128 B)
+// Per reduction chunk of 32 rows (r = channel x tap) every thread builds its im2col row (hi and lo tf32 parts) and a
+// share of the weight tile, a proxy fence publishes them to the async proxy, ONE thread issues 4 k-steps x 3 MMAs
+// (lo*hi, hi*lo, hi*hi) and commits to an mbarrier; the epilogue reads the accumulator with tcgen05.ld (lane = time
+// step, so the [B][C][T] stores are coalesced) and fuses bias + residual.
+// ------------------------------------------------------------------------------------------------
+constexpr int T5_M = 128, T5_RC = 32;
+
+__device__ __forceinline__ uint64_t t5_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp): start [0,14) >>4, LBO [16,30) >>4, SBO [32,46) >>4,
+    // version [46,48) = 1, layout_type [61,64) = 0 (SWIZZLE_NONE)
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void t5_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(256) conv1d_t5_kernel(ConvParams p, int xsp, int N) {
+    extern __shared__ __align__(128) unsigned char t5sm[];
+    // [A_hi 16K][A_lo 16K][B_hi N*128][B_lo N*128][slab][roff][mbar][tmem slot]
+    float* a_hi = reinterpret_cast<float*>(t5sm);
+    float* a_lo = a_hi + T5_M * T5_RC;
+    float* b_hi = a_lo + T5_M * T5_RC;
+    float* b_lo = b_hi + N * T5_RC;
+    float* xs = b_lo + N * T5_RC;
+    int* roff = reinterpret_cast<int*>(xs + p.ci_chunk * xsp);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(roff + T5_RC);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * T5_M, co0 = blockIdx.y * N, b = blockIdx.z;
+    const float* xb = p.x + (size_t)b * p.c_in * p.t_in;
+    const uint32_t ncols = N < 32 ? 32u : (uint32_t)N;   // power of two >= 32
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32_(tslot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32_(mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tslot;
+
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T5_M >> 4) << 24);
+    const uint32_t lbo_a = (T5_M / 8) * 128, lbo_b = (uint32_t)(N / 8) * 128;
+    const uint32_t a_hi_s = smem_u32_(a_hi), a_lo_s = smem_u32_(a_lo), b_hi_s = smem_u32_(b_hi), b_lo_s = smem_u32_(b_lo);
+
+    const int g0 = t0 * p.stride - p.pad_left;
+    uint32_t phase = 0, first = 1;
+    for (int ci0 = 0; ci0 < p.c_in; ci0 += p.ci_chunk) {
+        const int nci = min(p.ci_chunk, p.c_in - ci0);
+        const int rc = nci * p.K;
+        // (the previous chunk's MMAs have completed -- waited below -- so every buffer may be rewritten)
+        for (int r = tid; r < T5_RC; r += 256) {
+            int off = 0;
+            if (r < rc) {
+                const int cl = r / p.K, k = r - cl * p.K, kd = k * p.dil;
+                off = cl * xsp + (kd % p.stride) * p.PL + kd / p.stride;
+            }
+            roff[r] = off;
+        }
+        for (int cl = warp; cl < nci; cl += 8) {
+            const float* xrow = xb + (size_t)(ci0 + cl) * p.t_in;
+            float* xdst = xs + cl * xsp;
+            if (p.stride == 1) {
+                for (int j = lane; j < p.span; j += 32)
+                    xdst[j] = conv_fetch(xrow, g0 + j, p.t_in, p.t_virt, p.reflect, p.elu);
+            } else {
+                for (int ph = 0; ph < p.stride; ++ph)
+                    for (int q = lane; q * p.stride + ph < p.span; q += 32)
+                        xdst[ph * p.PL + q] = conv_fetch(xrow, g0 + q * p.stride + ph, p.t_in, p.t_virt, p.reflect, p.elu);
+            }
+        }
+        // weight tile B[co][r] (hi, lo), canonical K-major: thread handles (r, co) with co fastest (coalesced global reads)
+        for (int idx = tid; idx < T5_RC * N; idx += 256) {
+            const int r = idx / N, cc = idx - r * N;
+            const float w = (r < rc && co0 + cc < p.c_out) ? p.w[((size_t)ci0 * p.K + r) * p.c_out + co0 + cc] : 0.f;
+            const uint32_t hi = to_tf32(w);
+            const int o = (r >> 2) * (N / 8) * 32 + (cc >> 3) * 32 + (cc & 7) * 4 + (r & 3);   // in floats
+            b_hi[o] = __uint_as_float(hi);
+            b_lo[o] = __uint_as_float(to_tf32(w - __uint_as_float(hi)));
+        }
+        __syncthreads();   // slab + roff ready
+        // im2col tile A[t][r] (hi, lo): threads 0..127 own one time step each for r in [0,16), threads 128..255 for [16,32)
+        {
+            const int t = tid & 127, rbase = (tid >> 7) * 16;
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {   // 16-byte k-chunks of 4 reduction rows
+                float4 vh, vl;
+                float xv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) xv[e] = xs[roff[rbase + kc * 4 + e] + t];
+                uint32_t h0 = to_tf32(xv[0]), h1 = to_tf32(xv[1]), h2 = to_tf32(xv[2]), h3 = to_tf32(xv[3]);
+                vh = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+                vl = make_float4(__uint_as_float(to_tf32(xv[0] - vh.x)), __uint_as_float(to_tf32(xv[1] - vh.y)),
+                                 __uint_as_float(to_tf32(xv[2] - vh.z)), __uint_as_float(to_tf32(xv[3] - vh.w)));
+                const int o = ((rbase >> 2) + kc) * (T5_M / 8) * 32 + (t >> 3) * 32 + (t & 7) * 4;   // in floats
+                *reinterpret_cast<float4*>(a_hi + o) = vh;
+                *reinterpret_cast<float4*>(a_lo + o) = vl;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int ks = 0; ks < T5_RC / 8; ++ks) {   // one instruction = 8 reduction rows = two 16-byte k-chunks
+                const uint64_t ah = t5_desc(a_hi_s + ks * 2 * lbo_a, lbo_a), al = t5_desc(a_lo_s + ks * 2 * lbo_a, lbo_a);
+                const uint64_t bh = t5_desc(b_hi_s + ks * 2 * lbo_b, lbo_b), bl = t5_desc(b_lo_s + ks * 2 * lbo_b, lbo_b);
+                t5_mma(tmem, al, bh, idesc, first ? 0u : 1u);
+                first = 0;
+                t5_mma(tmem, ah, bl, idesc, 1u);
+                t5_mma(tmem, ah, bh, idesc, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32_(mbar)) : "memory");
+        }
+        {   // everyone waits for the tensor core to finish reading this chunk's tiles
+            uint32_t ok = 0;
+            do {
+                asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n selp.u32 %0, 1, 0, q;\n}"
+                             : "=r"(ok) : "r"(smem_u32_(mbar)), "r"(phase) : "memory");
+            } while (!ok);
+            phase ^= 1u;
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp < 4) {   // warp w reads TMEM lanes [32w, 32w+32) = time steps; 16 output channels per load
+        const int t = t0 + warp * 32 + lane;
+        for (int c0 = 0; c0 < N; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (p.tr_S == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int co = co0 + c0 + j;
+                    if (co < p.c_out && t < p.t_out) {
+                        const size_t o = ((size_t)b * p.c_out + co) * p.t_out + t;
+                        float y = __uint_as_float(v[j]) + (p.bias ? p.bias[co] : 0.f);
+                        if (p.res) y += p.res[o];
+                        p.y[o] = y;
+                    }
+                }
+            } else {   // transposed conv: column n' = co*S + phase, output step = t*S + phase - trim
+                const int cout = p.c_out / p.tr_S;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = co0 + c0 + j;
+                    if (n < p.c_out && t < p.t_out) {
+                        const int co = n / p.tr_S, ph = n - co * p.tr_S, o = t * p.tr_S + ph - p.tr_trim;
+                        if (o >= 0 && o < p.tr_tout)
+                            p.y[((size_t)b * cout + co) * p.tr_tout + o] = __uint_as_float(v[j]) + (p.bias ? p.bias[co] : 0.f);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
+}
+
+static int launch_conv1d_t5(const ConvParams& p, int batch, cudaStream_t s) {
+    ConvParams q = p;
+    q.ci_chunk = max(1, min(p.c_in, T5_RC / p.K));
+    q.span = (T5_M - 1) * p.stride + (p.K - 1) * p.dil + 1;
+    q.PL = acb_ceil_div(q.span, p.stride);
+    const int xsp = p.stride * q.PL;
+    const int N = p.c_out >= 256 ? 256 : (p.c_out >= 128 ? 128 : (p.c_out >= 64 ? 64 : 32));
+    size_t smem = ((size_t)2 * T5_M * T5_RC + (size_t)2 * N * T5_RC + (size_t)q.ci_chunk * xsp) * sizeof(float) +
+                  T5_RC * sizeof(int) + 8 + 8;
+    ACB_REQUIRE(smem <= 200 * 1024, "acb_conv1d: tcgen05 tile needs %zu B of shared memory", smem);
+    ACB_CHECK_CUDA(cudaFuncSetAttribute(conv1d_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(acb_ceil_div(p.t_out, T5_M), acb_ceil_div(p.c_out, N), batch);
+    conv1d_t5_kernel<<<grid, 256, smem, s>>>(q, xsp, N);
+    ACB_LAUNCH_CHECK();
+    return ACB_OK;
+}
+
 // Few output channels (the decoder's last conv, Cout = audio channels): a thread owns 4 consecutive output steps of
 // every output channel and slides a register window over the taps, so the kernel is a pure stream over x.
 constexpr int SC_MAXCO = 4, SC_TILE = 1024;
@@ -390,15 +585,21 @@ extern "C" int acb_conv1d(const float* x, const float* w_packed, const float* bi
     ACB_REQUIRE(t_virtual >= t_in, "acb_conv1d: t_virtual < t_in");
     ACB_REQUIRE(batch <= 65535, "acb_conv1d: batch > 65535");
     ConvParams p{x, w_packed, bias, residual, y, c_in, c_out, t_in, t_virtual, t_out, kernel, stride, dilation,
-                 pad_left, reflect, elu_in, 0, 0, 0};
+                 pad_left, reflect, elu_in, 0, 0, 0, 0, 0, 0};
     cudaStream_t s = (cudaStream_t)stream;
     if (c_out <= SC_MAXCO && stride == 1 && dilation == 1 && (kernel == 7 || kernel == 3)) {
         SmallCoParams q{x, w_packed, bias, residual, y, c_in, c_out, t_in, t_virtual, t_out, kernel, pad_left, reflect, elu_in, 0};
         return kernel == 7 ? launch_small_cout<7>(q, batch, s) : launch_small_cout<3>(q, batch, s);
     }
-    ACB_REQUIRE(precision == ACB_CONV_FP32 || precision == ACB_CONV_TF32X3, "acb_conv1d: unknown precision %d", precision);
-    // tensor pipe (3xTF32) when asked for and the layer has enough channels / reduction depth to fill the MMA tiles
-    if (precision == ACB_CONV_TF32X3 && c_out >= 32 && c_in * kernel >= 16) return launch_conv1d_tc(p, batch, s);
+    ACB_REQUIRE(precision >= ACB_CONV_FP32 && precision <= ACB_CONV_TF32X3_MMASYNC, "acb_conv1d: unknown precision %d", precision);
+    // tensor pipe (3xTF32) when asked for and the layer has enough channels / reduction depth to fill the MMA tiles:
+    // tcgen05 + TMEM by default, the legacy mma.sync kernel on request
+    if (precision != ACB_CONV_FP32 && c_out >= 32 && c_in * kernel >= 16 && kernel <= T5_RC) {
+        // tcgen05 pays a fixed im2col-tile build per 32 reduction rows: it wins once the tile has >= 128 output channels
+        // to amortise it over; narrower layers are faster on the mma.sync kernel (profiles/r1_perf_encodec_v4*.log)
+        if (precision == ACB_CONV_TF32X3 && c_out >= 128 && c_in * kernel >= 128) return launch_conv1d_t5(p, batch, s);
+        return launch_conv1d_tc(p, batch, s);
+    }
     const bool wide = t_out >= 2048;   // 8 output steps per thread once there is enough time axis to fill the tile
     if (c_out >= 64) return wide ? launch_conv1d<8, 8>(p, batch, s) : launch_conv1d<8, 4>(p, batch, s);
     if (c_out >= 32) return wide ? launch_conv1d<4, 8>(p, batch, s) : launch_conv1d<4, 4>(p, batch, s);
@@ -488,15 +689,24 @@ static int launch_convtr(const ConvTrParams& p, int batch, cudaStream_t s) {
     return ACB_OK;
 }
 
-extern "C" int acb_convtr1d(const float* x, const float* w_packed, const float* bias, float* y, int batch, int c_in,
-                            int c_out, int t_in, int t_out, int kernel, int stride, int trim_left, int elu_in,
-                            void* stream) {
+extern "C" int acb_convtr1d(const float* x, const float* w_packed, const float* w_gemm, const float* bias, float* y, int batch,
+                            int c_in, int c_out, int t_in, int t_out, int kernel, int stride, int trim_left, int elu_in,
+                            int precision, void* stream) {
     ACB_REQUIRE(x && w_packed && y, "acb_convtr1d: null pointer");
     ACB_REQUIRE(batch > 0 && batch <= 65535 && c_in > 0 && c_out > 0 && t_in > 0 && t_out > 0, "acb_convtr1d: bad shape");
     ACB_REQUIRE(kernel == 2 * stride, "acb_convtr1d: only kernel == 2*stride is built (got k=%d s=%d)", kernel, stride);
     ACB_REQUIRE(trim_left >= 0 && t_out + trim_left <= (t_in + 1) * stride, "acb_convtr1d: trim out of range");
-    ConvTrParams p{x, w_packed, bias, y, c_in, c_out, t_in, t_out, trim_left, elu_in, 0};
+    ACB_REQUIRE(precision >= ACB_CONV_FP32 && precision <= ACB_CONV_TF32X3_MMASYNC, "acb_convtr1d: unknown precision %d", precision);
     cudaStream_t s = (cudaStream_t)stream;
+    if (precision == ACB_CONV_TF32X3 && w_gemm && c_out * stride >= 128 && c_in >= 64) {
+        // y[co][ti*S + ph - trim] = sum_{ci} x[ci][ti] w[ci][ph][co] + x[ci][ti-1] w[ci][ph+S][co]: a GEMM over 2-tap im2col
+        // rows r = (ci, k) (k = 0: x[ti-1], k = 1: x[ti]) and virtual channels n' = co*S + ph; w_gemm is [2*Cin][Cout*S]
+        const int n_ti = acb_ceil_div(t_out + trim_left, stride);
+        ConvParams p{x, w_gemm, bias, nullptr, y, c_in, c_out * stride, t_in, t_in, n_ti, 2, 1, 1, 1, 0, elu_in, 0, 0, 0,
+                     stride, trim_left, t_out};
+        return launch_conv1d_t5(p, batch, s);
+    }
+    ConvTrParams p{x, w_packed, bias, y, c_in, c_out, t_in, t_out, trim_left, elu_in, 0};
     switch (stride) {
         case 2: return launch_convtr<2>(p, batch, s);
         case 3: return launch_convtr<3>(p, batch, s);

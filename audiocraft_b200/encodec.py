@@ -125,7 +125,7 @@ class EncodecModel(CompressionModel):
         defaults to fp32 so that RVQ indices equal the fp32 reference's; the decoder's output is a waveform checked to a
         tolerance (1e-4) and defaults to the faster 3xTF32 convolutions."""
         self.device = _lib.require_cuda(device)
-        prec = {'fp32': _lib.CONV_FP32, 'tf32x3': _lib.CONV_TF32X3}
+        prec = {'fp32': _lib.CONV_FP32, 'tf32x3': _lib.CONV_TF32X3, 'tf32x3_mmasync': _lib.CONV_TF32X3_MMASYNC}
         self._enc_prec, self._dec_prec = prec[encoder_precision], prec[decoder_precision]
         self._lib = _lib.lib()
         self.cfg = dict(cfg)
@@ -174,6 +174,10 @@ class EncodecModel(CompressionModel):
         elif layer['kind'] == 'convtr':
             w = self._fold(sd, p)                                       # [Cin][Cout][K]
             out['w'] = w.permute(0, 2, 1).contiguous()                  # [Cin][K][Cout]
+            cin, cout, k = w.shape
+            S = layer['stride']
+            # GEMM operand of the tcgen05 path: [2*Cin][Cout*S], row (ci, k'), column co*S + ph, value w[ci][co][ph + (1-k')*S]
+            out['w_gemm'] = w.view(cin, cout, 2, S).flip(2).permute(0, 2, 1, 3).reshape(cin * 2, cout * S).contiguous()
             out['b'] = sd[p + 'bias'].to(self.device, torch.float32).contiguous()
         else:
             out['w_ih'], out['w_hh'], out['bias'] = [], [], []
@@ -202,13 +206,13 @@ class EncodecModel(CompressionModel):
         self.launches += 1
         return y
 
-    def _convtr(self, x, L):
+    def _convtr(self, x, L, prec=0):
         B, cin, T = x.shape
         trim_left, t_out = convtr_geometry(T, L['k'], L['stride'], self.causal, self.cfg['trim_right_ratio'])
         y = torch.empty((B, L['cout'], t_out), device=x.device, dtype=torch.float32)
-        _lib.check(self._lib.acb_convtr1d(_lib.ptr(x), _lib.ptr(L['w']), _lib.ptr(L['b']), _lib.ptr(y), B, cin,
-                                          L['cout'], T, t_out, L['k'], L['stride'], trim_left, int(L['elu']),
-                                          _lib.stream()), 'convtr1d')
+        _lib.check(self._lib.acb_convtr1d(_lib.ptr(x), _lib.ptr(L['w']), _lib.ptr(L['w_gemm']), _lib.ptr(L['b']),
+                                          _lib.ptr(y), B, cin, L['cout'], T, t_out, L['k'], L['stride'], trim_left,
+                                          int(L['elu']), prec, _lib.stream()), 'convtr1d')
         self.launches += 1
         return y
 
@@ -246,7 +250,7 @@ class EncodecModel(CompressionModel):
                 res = skip if L['res'] == 'out' else None
                 x = self._conv(x, L, res=res, prec=prec)
             elif L['kind'] == 'convtr':
-                x = self._convtr(x, L)
+                x = self._convtr(x, L, prec=prec)
             else:
                 x = self._lstm(x, L, prec=prec)
             if prof is not None:

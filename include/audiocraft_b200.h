@@ -63,16 +63,21 @@ int acb_conv1d(const float* x, const float* w_packed, const float* bias, const f
  * operand split into two tf32 terms and three MMAs per product (~2^-22 relative error per product, fp32 accumulate) --
  * layers too small for the MMA tile fall back to fp32 FMA. */
 #define ACB_CONV_FP32 0
-#define ACB_CONV_TF32X3 1
+#define ACB_CONV_TF32X3 1          /* tcgen05.mma.kind::tf32, accumulator in TMEM */
+#define ACB_CONV_TF32X3_MMASYNC 2  /* same arithmetic on the legacy mma.sync.m16n8k8 path */
 
 /* StreamableConvTranspose1d.forward, audiocraft/modules/conv.py:221-243: transposed conv (kernel = 2*stride)
  * followed by the fixed trim, computed directly in trimmed coordinates:
  *   y[b,co,o] = bias[co] + sum_ci ( act(x[b,ci,ti]) * w[ci][p][co] + act(x[b,ci,ti-1]) * w[ci][p+stride][co] ),
  *   u = o + trim_left, ti = u / stride, p = u % stride, x outside [0,t_in) = 0.
  * w_packed is [Cin][K][Cout].  Supported strides: 2,3,4,5,8 with kernel == 2*stride. */
-int acb_convtr1d(const float* x, const float* w_packed, const float* bias, float* y,
+int acb_convtr1d(const float* x, const float* w_packed, const float* w_gemm, const float* bias, float* y,
                  int batch, int c_in, int c_out, int t_in, int t_out, int kernel, int stride, int trim_left,
-                 int elu_in, void* stream);
+                 int elu_in, int precision, void* stream);
+/* w_gemm (optional, needed for precision ACB_CONV_TF32X3): the same weights packed as the GEMM operand
+ * [2*Cin][Cout*stride], row r = ci*2 + k (k = 0 multiplies x[ti-1], k = 1 multiplies x[ti]), column n' = co*stride + ph,
+ * value w[ci][ph + (1-k)*stride][co]: the transposed conv then runs on the tcgen05 kernel as one GEMM whose accumulator
+ * row (TMEM lane) ti holds `stride` consecutive output steps of every channel. */
 
 /* Recurrent half of StreamableLSTM.forward, audiocraft/modules/lstm.py:19-25 (nn.LSTM, gate order i,f,g,o,
  * zero initial state).  The input half (W_ih x_t + b_ih + b_hh for every t) is a 1x1 acb_conv1d producing

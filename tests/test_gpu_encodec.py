@@ -36,7 +36,7 @@ def test_conv1d_matches_oracle(cin, cout, k, s, d, causal, L):
     x = torch.randn(2, cin, L, generator=g)
     w = torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5
     b = torch.randn(cout, generator=g)
-    for elu, with_res, prec in [(False, False, 0), (True, True, 0), (True, True, 1), (False, False, 1)]:
+    for elu, with_res, prec in [(False, False, 0), (True, True, 0), (True, True, 1), (False, False, 1), (True, True, 2)]:
         ref = EO.sconv1d(EO.elu(x) if elu else x, w, b, stride=s, dilation=d, causal=causal)
         res = torch.randn(ref.shape, generator=g) if with_res else None
         if with_res:
@@ -55,6 +55,7 @@ def test_conv1d_matches_oracle(cin, cout, k, s, d, causal, L):
 @pytest.mark.parametrize('cin,cout,s,causal,ratio,L', [
     (16, 8, 2, False, 1.0, 37), (8, 16, 3, True, 1.0, 20), (32, 16, 4, False, 1.0, 101), (12, 6, 5, False, 1.0, 50),
     (64, 32, 8, False, 1.0, 50), (8, 4, 4, True, 0.5, 33), (8, 4, 8, True, 0.0, 1), (70, 66, 4, False, 1.0, 70),
+    (128, 64, 4, False, 1.0, 300), (96, 40, 5, False, 1.0, 131), (64, 16, 8, True, 1.0, 257), (256, 128, 2, True, 0.5, 129),
 ])
 def test_convtr1d_matches_oracle(cin, cout, s, causal, ratio, L):
     from audiocraft_b200.encodec import convtr_geometry
@@ -66,11 +67,13 @@ def test_convtr1d_matches_oracle(cin, cout, s, causal, ratio, L):
     ref = EO.sconvtr1d(EO.elu(x), w, b, s, causal, ratio)
     tl, tout = convtr_geometry(L, 2 * s, s, causal, ratio)
     assert tout == ref.shape[-1] == L * s
-    y = torch.empty(2, cout, tout, device='cuda')
     xd, wd, bd = _dev(x), _dev(w.permute(0, 2, 1)), _dev(b)   # keep the device tensors alive across the launch
-    lib.check(L_.acb_convtr1d(lib.ptr(xd), lib.ptr(wd), lib.ptr(bd), lib.ptr(y), 2, cin,
-                              cout, L, tout, 2 * s, s, tl, 1, lib.stream()))
-    torch.testing.assert_close(y.cpu(), ref, rtol=1e-4, atol=1e-4)
+    wg = _dev(w.view(cin, cout, 2, s).flip(2).permute(0, 2, 1, 3).reshape(cin * 2, cout * s))
+    for prec in (0, 1):   # fp32 FMA; 3xTF32 on tcgen05 as one GEMM over virtual channels (when the layer is big enough)
+        y = torch.empty(2, cout, tout, device='cuda')
+        lib.check(L_.acb_convtr1d(lib.ptr(xd), lib.ptr(wd), lib.ptr(wg), lib.ptr(bd), lib.ptr(y), 2, cin,
+                                  cout, L, tout, 2 * s, s, tl, 1, prec, lib.stream()))
+        torch.testing.assert_close(y.cpu(), ref, rtol=1e-4, atol=1e-4)
 
 
 def test_weight_norm_fold_matches_oracle():
