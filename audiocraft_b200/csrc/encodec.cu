@@ -324,22 +324,37 @@ __device__ __forceinline__ void t5_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-__global__ void __launch_bounds__(256) conv1d_t5_kernel(ConvParams p, int xsp, int N) {
+// TERMS = 2: x ~ hi + lo -> 3 MMAs per product (lo*hi, hi*lo, hi*hi).  (A 3-term / 6-MMA split was measured: identical
+// end-to-end error, 1.43e-4 on the 32 kHz latents -- the residual is the tensor core's accumulate rounding, not the
+// operand split -- so only the 2-term variant is built.)
+constexpr int T5_SLAB_PT = 16;   // staged input elements per thread and chunk (<= 4096 per chunk)
+
+template <int TERMS>
+__device__ __forceinline__ void t5_split(float x, float (&out)[TERMS]) {
+    float rem = x;
+#pragma unroll
+    for (int i = 0; i < TERMS; ++i) {
+        out[i] = __uint_as_float(to_tf32(rem));
+        rem -= out[i];
+    }
+}
+
+template <int TERMS, int NW>   // NW = weight elements per thread and chunk = N * 32 / 256
+__global__ void __launch_bounds__(256, 2) conv1d_t5_kernel(ConvParams p, int xsp) {
+    constexpr int N = NW * 8;
     extern __shared__ __align__(128) unsigned char t5sm[];
-    // [A_hi 16K][A_lo 16K][B_hi N*128][B_lo N*128][slab][roff][mbar][tmem slot]
-    float* a_hi = reinterpret_cast<float*>(t5sm);
-    float* a_lo = a_hi + T5_M * T5_RC;
-    float* b_hi = a_lo + T5_M * T5_RC;
-    float* b_lo = b_hi + N * T5_RC;
-    float* xs = b_lo + N * T5_RC;
-    int* roff = reinterpret_cast<int*>(xs + p.ci_chunk * xsp);
+    // [A terms: TERMS x 16 KB][B terms: TERMS x N*128 B][slab][roff][mbar][tmem slot]
+    float* a_t = reinterpret_cast<float*>(t5sm);
+    float* b_t = a_t + TERMS * T5_M * T5_RC;
+    float* xs = b_t + TERMS * N * T5_RC;
+    int* roff = reinterpret_cast<int*>(xs + ((p.ci_chunk * xsp + 3) & ~3));   // keep 16-byte alignment behind the slab
     uint64_t* mbar = reinterpret_cast<uint64_t*>(roff + T5_RC);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t0 = blockIdx.x * T5_M, co0 = blockIdx.y * N, b = blockIdx.z;
     const float* xb = p.x + (size_t)b * p.c_in * p.t_in;
-    const uint32_t ncols = N < 32 ? 32u : (uint32_t)N;   // power of two >= 32
+    constexpr uint32_t ncols = N < 32 ? 32u : (uint32_t)N;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32_(tslot)), "r"(ncols) : "memory");
@@ -349,67 +364,83 @@ __global__ void __launch_bounds__(256) conv1d_t5_kernel(ConvParams p, int xsp, i
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32_(mbar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // ---- chunk-invariant staging maps: where each of this thread's slab elements comes from (relative to the first
+    //      channel of a chunk) and where it goes (phase-de-interleaved slab), computed once
+    const int g0 = t0 * p.stride - p.pad_left;
+    int src_off[T5_SLAB_PT], dcl[T5_SLAB_PT];   // dcl = slab destination | (channel-in-chunk << 24), -1 = no element
+    const int n_slab = p.ci_chunk * p.span;
+#pragma unroll
+    for (int i = 0; i < T5_SLAB_PT; ++i) {
+        const int e = tid + 256 * i;
+        src_off[i] = -1; dcl[i] = -1;
+        if (e < n_slab) {
+            const int cl = e / p.span, j = e - cl * p.span;
+            int g = g0 + j;
+            if (p.reflect) {
+                if (g < 0) g = -g;
+                if (g >= p.t_virt) g = 2 * (p.t_virt - 1) - g;
+            }
+            dcl[i] = (cl * xsp + (p.stride == 1 ? j : (j % p.stride) * p.PL + j / p.stride)) | (cl << 24);
+            if (g >= 0 && g < p.t_in) src_off[i] = cl * p.t_in + g;   // else: padding -> 0
+        }
+    }
+    for (int r = tid; r < T5_RC; r += 256) {   // reduction row r = (channel, tap) -> slab offset (chunk-invariant too)
+        const int cl = r / p.K, k = r - cl * p.K, kd = k * p.dil;
+        roff[r] = cl < p.ci_chunk ? cl * xsp + (kd % p.stride) * p.PL + kd / p.stride : 0;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tslot;
 
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T5_M >> 4) << 24);
-    const uint32_t lbo_a = (T5_M / 8) * 128, lbo_b = (uint32_t)(N / 8) * 128;
-    const uint32_t a_hi_s = smem_u32_(a_hi), a_lo_s = smem_u32_(a_lo), b_hi_s = smem_u32_(b_hi), b_lo_s = smem_u32_(b_lo);
+    constexpr uint32_t lbo_a = (T5_M / 8) * 128, lbo_b = (uint32_t)(N / 8) * 128;
+    const uint32_t a_s = smem_u32_(a_t), b_s = smem_u32_(b_t);
 
-    const int g0 = t0 * p.stride - p.pad_left;
+    float xr[T5_SLAB_PT], wr[NW];
+    auto prefetch = [&](int ci0) {   // raw global values of one chunk into registers (no dependence on smem state)
+        const int nci = min(p.ci_chunk, p.c_in - ci0), rc = nci * p.K;
+        const float* xc = xb + (size_t)ci0 * p.t_in;
+#pragma unroll
+        for (int i = 0; i < T5_SLAB_PT; ++i)
+            xr[i] = (src_off[i] >= 0 && (dcl[i] >> 24) < nci) ? __ldg(xc + src_off[i]) : 0.f;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const int idx = tid + 256 * i, r = idx / N, cc = idx % N;
+            wr[i] = (r < rc && co0 + cc < p.c_out) ? __ldg(p.w + ((size_t)ci0 * p.K + r) * p.c_out + co0 + cc) : 0.f;
+        }
+    };
+    prefetch(0);
+
     uint32_t phase = 0, first = 1;
     for (int ci0 = 0; ci0 < p.c_in; ci0 += p.ci_chunk) {
-        const int nci = min(p.ci_chunk, p.c_in - ci0);
-        const int rc = nci * p.K;
-        // (the previous chunk's MMAs have completed -- waited below -- so every buffer may be rewritten)
-        for (int r = tid; r < T5_RC; r += 256) {
-            int off = 0;
-            if (r < rc) {
-                const int cl = r / p.K, k = r - cl * p.K, kd = k * p.dil;
-                off = cl * xsp + (kd % p.stride) * p.PL + kd / p.stride;
-            }
-            roff[r] = off;
+        // (the previous chunk's MMAs have completed -- waited at the bottom -- so slab and tiles may be rewritten)
+#pragma unroll
+        for (int i = 0; i < T5_SLAB_PT; ++i)
+            if (dcl[i] >= 0) xs[dcl[i] & 0xFFFFFF] = p.elu ? acb_elu(xr[i]) : xr[i];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const int idx = tid + 256 * i, r = idx / N, cc = idx % N;
+            float parts[TERMS];
+            t5_split<TERMS>(wr[i], parts);
+            const int o = (r >> 2) * (N / 8) * 32 + (cc >> 3) * 32 + (cc & 7) * 4 + (r & 3);   // canonical K-major, in floats
+#pragma unroll
+            for (int q = 0; q < TERMS; ++q) b_t[q * N * T5_RC + o] = parts[q];
         }
-        for (int cl = warp; cl < nci; cl += 8) {
-            const float* xrow = xb + (size_t)(ci0 + cl) * p.t_in;
-            float* xdst = xs + cl * xsp;
-            if (p.stride == 1) {
-                for (int j = lane; j < p.span; j += 32)
-                    xdst[j] = conv_fetch(xrow, g0 + j, p.t_in, p.t_virt, p.reflect, p.elu);
-            } else {
-                for (int ph = 0; ph < p.stride; ++ph)
-                    for (int q = lane; q * p.stride + ph < p.span; q += 32)
-                        xdst[ph * p.PL + q] = conv_fetch(xrow, g0 + q * p.stride + ph, p.t_in, p.t_virt, p.reflect, p.elu);
-            }
-        }
-        // weight tile B[co][r] (hi, lo), canonical K-major: thread handles (r, co) with co fastest (coalesced global reads)
-        for (int idx = tid; idx < T5_RC * N; idx += 256) {
-            const int r = idx / N, cc = idx - r * N;
-            const float w = (r < rc && co0 + cc < p.c_out) ? p.w[((size_t)ci0 * p.K + r) * p.c_out + co0 + cc] : 0.f;
-            const uint32_t hi = to_tf32(w);
-            const int o = (r >> 2) * (N / 8) * 32 + (cc >> 3) * 32 + (cc & 7) * 4 + (r & 3);   // in floats
-            b_hi[o] = __uint_as_float(hi);
-            b_lo[o] = __uint_as_float(to_tf32(w - __uint_as_float(hi)));
-        }
-        __syncthreads();   // slab + roff ready
-        // im2col tile A[t][r] (hi, lo): threads 0..127 own one time step each for r in [0,16), threads 128..255 for [16,32)
-        {
+        if (ci0 + p.ci_chunk < p.c_in) prefetch(ci0 + p.ci_chunk);   // next chunk's global loads fly during build + MMA
+        __syncthreads();   // slab ready
+        {   // im2col tile A[t][r]: threads 0..127 own one time step each for r in [0,16), threads 128..255 for [16,32)
             const int t = tid & 127, rbase = (tid >> 7) * 16;
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) {   // 16-byte k-chunks of 4 reduction rows
-                float4 vh, vl;
-                float xv[4];
+                float parts[4][TERMS];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) xv[e] = xs[roff[rbase + kc * 4 + e] + t];
-                uint32_t h0 = to_tf32(xv[0]), h1 = to_tf32(xv[1]), h2 = to_tf32(xv[2]), h3 = to_tf32(xv[3]);
-                vh = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
-                vl = make_float4(__uint_as_float(to_tf32(xv[0] - vh.x)), __uint_as_float(to_tf32(xv[1] - vh.y)),
-                                 __uint_as_float(to_tf32(xv[2] - vh.z)), __uint_as_float(to_tf32(xv[3] - vh.w)));
+                for (int e = 0; e < 4; ++e) t5_split<TERMS>(xs[roff[rbase + kc * 4 + e] + t], parts[e]);
                 const int o = ((rbase >> 2) + kc) * (T5_M / 8) * 32 + (t >> 3) * 32 + (t & 7) * 4;   // in floats
-                *reinterpret_cast<float4*>(a_hi + o) = vh;
-                *reinterpret_cast<float4*>(a_lo + o) = vl;
+#pragma unroll
+                for (int q = 0; q < TERMS; ++q)
+                    *reinterpret_cast<float4*>(a_t + q * T5_M * T5_RC + o) =
+                        make_float4(parts[0][q], parts[1][q], parts[2][q], parts[3][q]);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -418,12 +449,20 @@ __global__ void __launch_bounds__(256) conv1d_t5_kernel(ConvParams p, int xsp, i
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ks = 0; ks < T5_RC / 8; ++ks) {   // one instruction = 8 reduction rows = two 16-byte k-chunks
-                const uint64_t ah = t5_desc(a_hi_s + ks * 2 * lbo_a, lbo_a), al = t5_desc(a_lo_s + ks * 2 * lbo_a, lbo_a);
-                const uint64_t bh = t5_desc(b_hi_s + ks * 2 * lbo_b, lbo_b), bl = t5_desc(b_lo_s + ks * 2 * lbo_b, lbo_b);
-                t5_mma(tmem, al, bh, idesc, first ? 0u : 1u);
-                first = 0;
-                t5_mma(tmem, ah, bl, idesc, 1u);
-                t5_mma(tmem, ah, bh, idesc, 1u);
+                uint64_t ad[TERMS], bd[TERMS];
+#pragma unroll
+                for (int q = 0; q < TERMS; ++q) {
+                    ad[q] = t5_desc(a_s + q * (T5_M * T5_RC * 4) + ks * 2 * lbo_a, lbo_a);
+                    bd[q] = t5_desc(b_s + q * (N * T5_RC * 4) + ks * 2 * lbo_b, lbo_b);
+                }
+                // smallest cross terms first; term index 0 = hi.  Keep products a_i * b_j with i + j < TERMS.
+#pragma unroll
+                for (int sum = TERMS - 1; sum >= 0; --sum)
+#pragma unroll
+                    for (int i = 0; i <= sum; ++i) {
+                        t5_mma(tmem, ad[i], bd[sum - i], idesc, first ? 0u : 1u);
+                        first = 0;
+                    }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32_(mbar)) : "memory");
         }
@@ -477,21 +516,30 @@ __global__ void __launch_bounds__(256) conv1d_t5_kernel(ConvParams p, int xsp, i
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
 }
 
+template <int TERMS, int NW>
+static int launch_t5_one(const ConvParams& q, int xsp, int batch, cudaStream_t s) {
+    constexpr int N = NW * 8;
+    size_t smem = ((size_t)TERMS * T5_M * T5_RC + (size_t)TERMS * N * T5_RC + (size_t)((q.ci_chunk * xsp + 3) & ~3)) * sizeof(float) +
+                  T5_RC * sizeof(int) + 8 + 8;
+    ACB_REQUIRE(smem <= 200 * 1024, "acb_conv1d: tcgen05 tile needs %zu B of shared memory", smem);
+    ACB_CHECK_CUDA(cudaFuncSetAttribute(conv1d_t5_kernel<TERMS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(acb_ceil_div(q.t_out, T5_M), acb_ceil_div(q.c_out, N), batch);
+    conv1d_t5_kernel<TERMS, NW><<<grid, 256, smem, s>>>(q, xsp);
+    ACB_LAUNCH_CHECK();
+    return ACB_OK;
+}
+
 static int launch_conv1d_t5(const ConvParams& p, int batch, cudaStream_t s) {
     ConvParams q = p;
     q.ci_chunk = max(1, min(p.c_in, T5_RC / p.K));
     q.span = (T5_M - 1) * p.stride + (p.K - 1) * p.dil + 1;
     q.PL = acb_ceil_div(q.span, p.stride);
     const int xsp = p.stride * q.PL;
-    const int N = p.c_out >= 256 ? 256 : (p.c_out >= 128 ? 128 : (p.c_out >= 64 ? 64 : 32));
-    size_t smem = ((size_t)2 * T5_M * T5_RC + (size_t)2 * N * T5_RC + (size_t)q.ci_chunk * xsp) * sizeof(float) +
-                  T5_RC * sizeof(int) + 8 + 8;
-    ACB_REQUIRE(smem <= 200 * 1024, "acb_conv1d: tcgen05 tile needs %zu B of shared memory", smem);
-    ACB_CHECK_CUDA(cudaFuncSetAttribute(conv1d_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(acb_ceil_div(p.t_out, T5_M), acb_ceil_div(p.c_out, N), batch);
-    conv1d_t5_kernel<<<grid, 256, smem, s>>>(q, xsp, N);
-    ACB_LAUNCH_CHECK();
-    return ACB_OK;
+    ACB_REQUIRE(q.ci_chunk * q.span <= 256 * T5_SLAB_PT, "acb_conv1d: tcgen05 slab too large (%d elements)", q.ci_chunk * q.span);
+    if (p.c_out >= 256) return launch_t5_one<2, 32>(q, xsp, batch, s);
+    if (p.c_out >= 128) return launch_t5_one<2, 16>(q, xsp, batch, s);
+    if (p.c_out >= 64) return launch_t5_one<2, 8>(q, xsp, batch, s);
+    return launch_t5_one<2, 4>(q, xsp, batch, s);
 }
 
 // Few output channels (the decoder's last conv, Cout = audio channels): a thread owns 4 consecutive output steps of
@@ -592,9 +640,8 @@ extern "C" int acb_conv1d(const float* x, const float* w_packed, const float* bi
         return kernel == 7 ? launch_small_cout<7>(q, batch, s) : launch_small_cout<3>(q, batch, s);
     }
     ACB_REQUIRE(precision >= ACB_CONV_FP32 && precision <= ACB_CONV_TF32X3_MMASYNC, "acb_conv1d: unknown precision %d", precision);
-    // tensor pipe (3xTF32) when asked for and the layer has enough channels / reduction depth to fill the MMA tiles:
-    // tcgen05 + TMEM by default, the legacy mma.sync kernel on request
-    if (precision != ACB_CONV_FP32 && c_out >= 32 && c_in * kernel >= 16 && kernel <= T5_RC) {
+    if ((precision == ACB_CONV_TF32X3 || precision == ACB_CONV_TF32X3_MMASYNC) && c_out >= 32 && c_in * kernel >= 16 &&
+        kernel <= T5_RC) {
         // tcgen05 pays a fixed im2col-tile build per 32 reduction rows: it wins once the tile has >= 128 output channels
         // to amortise it over; narrower layers are faster on the mma.sync kernel (profiles/r1_perf_encodec_v4*.log)
         if (precision == ACB_CONV_TF32X3 && c_out >= 128 && c_in * kernel >= 128) return launch_conv1d_t5(p, batch, s);

@@ -12,8 +12,13 @@ from audiocraft_b200.loaders import load_compression_model  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=32)
 ap.add_argument('--seconds', type=float, default=10.0)
+ap.add_argument('--enc', default='fp32')
+ap.add_argument('--dec', default='tf32x3')
 a = ap.parse_args()
-cm = load_compression_model('synthetic/encodec_32k')
+from audiocraft_b200 import synth  # noqa: E402
+from audiocraft_b200.encodec import EncodecModel  # noqa: E402
+_cfg = synth.ENCODEC_CONFIGS['encodec_32k']
+cm = EncodecModel(synth.synth_encodec_state_dict(_cfg, 0), _cfg, 'cuda', encoder_precision=a.enc, decoder_precision=a.dec)
 x = torch.randn(a.batch, 1, int(a.seconds * 32000), device='cuda') * 0.1
 for _ in range(2):
     codes, _ = cm.encode(x)

@@ -236,3 +236,24 @@ def test_interleave_stereo_wrapper_matches_reference_golden():
         assert torch.equal(l, c0)
     with pytest.raises(AssertionError):
         InterleaveStereoCompressionModel(mono).encode(x[:, :1].cuda())
+
+
+@pytest.mark.parametrize('name', ['encodec_24k', 'encodec_32k'])
+def test_tensor_core_encoder_mode(name):
+    """encoder_precision='tf32x3' (throughput mode): latents within 5e-4 of the fp32 reference (tensor-core accumulate
+    rounding grows through 15 layers + LSTM), codes equal wherever the oracle's margin is clear of that."""
+    from audiocraft_b200.encodec import EncodecModel
+    g = torch.load(os.path.join(H.GOLDEN_DIR, f'{name}.pt'), weights_only=False)
+    cfg = synth.ENCODEC_CONFIGS[name]
+    sd = synth.synth_encodec_state_dict(cfg, seed=g['wseed'])
+    x = H.audio_input(cfg, g['batch'], g['length'], g['xseed'])
+    m = EncodecModel(sd, cfg, encoder_precision='tf32x3')
+    lat = m.encode_latent(x.cuda()).cpu()
+    print(f'{name} tensor-core encoder latent max err {(lat - g["latent"]).abs().max():.2e}')
+    torch.testing.assert_close(lat, g['latent'], rtol=0, atol=5e-4)
+    codes, _ = m.encode(x)
+    _, margins = EO.rvq_encode(g['latent'], EO.codebooks_of(sd, cfg['n_q']), return_margin=True)
+    neq = codes.cpu() != g['codes']
+    first = neq.int().cumsum(1).eq(1) & neq
+    assert (margins[first].abs() < 5e-3).all()
+    assert (codes.cpu() == g['codes']).float().mean() > 0.98
