@@ -169,6 +169,9 @@ LM_CONFIGS: tp.Dict[str, dict] = {
     'musicgen_large': dict(dim=2048, num_heads=32, num_layers=48),
     'lm_tiny': dict(dim=128, num_heads=2, num_layers=2, card=64),
     'lm_mini': dict(dim=256, num_heads=4, num_layers=3, card=128, cond_dim=96),
+    # the released widths with only 2 layers: exercise the d = 1536 / 2048 GEMM tiling in tests without the full depth
+    'lm_medium_2l': dict(dim=1536, num_heads=24, num_layers=2, card=2048, cond_dim=64),
+    'lm_large_2l': dict(dim=2048, num_heads=32, num_layers=2, card=2048, cond_dim=64),
 }
 _LM_COMMON = dict(hidden_scale=4, n_q=4, card=2048, delays=[0, 1, 2, 3], max_period=10000.0,
                   positional_scale=1.0, cross_attention=True, cfg_coef=3.0, cond_dim=768)

@@ -227,3 +227,23 @@ def test_chain_kernel_mode_matches_default(monkeypatch):
     # same math, different split-K grouping -> fp16-rounding-level differences (CFG mixing amplifies them x3)
     torch.testing.assert_close(chain, base, rtol=0, atol=3e-2)
     assert (out == ref).float().mean() > 0.9
+
+
+@pytest.mark.parametrize('name,B', [('lm_medium_2l', 8), ('lm_large_2l', 4), ('lm_large_2l', 32)])
+def test_released_widths_match_oracle(name, B):
+    """MusicGen-medium / -large layer shapes (d = 1536 / 2048, 4d FFN, card 2048) at bench-like row counts
+    (rows = 16, 8 and 64 = BASELINE config 5 on one GPU), two layers deep: CFG-mixed logits vs the fp16-emulating oracle."""
+    cfg, sd, m = _model(name, 11)
+    _, _, cross = H.lm_condition(cfg, sd, B, 7, 3)
+    T = 4
+    g = torch.Generator().manual_seed(B)
+    seq = torch.randint(0, cfg['card'], (B, 4, T + 4), generator=g)
+    lg = m.teacher_forced_logits(seq, cross, cfg['cfg_coef']).cpu()
+    o = LO.LMOracle(sd, cfg, half_gemm=True)
+    rec = []
+    o.generate(None, cross, B, T, use_sampling=False, record_logits=rec, teacher=seq)
+    ref = torch.stack(rec)
+    print(f'{name} rows={2 * B}: max |logit diff| {(lg - ref).abs().max():.2e} on |logits| <= {ref.abs().max():.1f}')
+    torch.testing.assert_close(lg, ref, rtol=2e-2, atol=3e-2)
+    out = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=True, top_k=250, cross_attention_src=cross)
+    assert out.shape == (B, 4, T) and int(out.min()) >= 0 and int(out.max()) < cfg['card']
