@@ -237,7 +237,7 @@ class EncodecModel(CompressionModel):
         return inp
 
     def _run(self, x, layers, prec=0):
-        skip = None
+        skip, have_shortcut = None, False
         prof = getattr(self, '_profile', None)   # optional per-layer CUDA-event timing (profiles/perf_encodec.py)
         for L in layers:
             if prof is not None:
@@ -245,8 +245,17 @@ class EncodecModel(CompressionModel):
                 e0.record()
                 shape_in = tuple(x.shape)
             if L['kind'] == 'conv':
+                if L['res'] == 'shortcut':          # skip = conv1x1(block input); the block input itself is unchanged
+                    skip = self._conv(x, L, prec=prec)
+                    have_shortcut = True
+                    if prof is not None:
+                        e1.record()
+                        prof.append((L, shape_in, tuple(skip.shape), e0, e1))
+                    continue
                 if L['res'] == 'in':
-                    skip = x
+                    if not have_shortcut:
+                        skip = x
+                    have_shortcut = False
                 res = skip if L['res'] == 'out' else None
                 x = self._conv(x, L, res=res, prec=prec)
             elif L['kind'] == 'convtr':
@@ -459,3 +468,79 @@ def get_wrapped_compression_model(compression_model: CompressionModel, interleav
     if compression_model_n_q is not None:
         compression_model.set_num_codebooks(compression_model_n_q)
     return compression_model
+
+
+# ----------------------------------------------------------------------------- HuggingFace-format checkpoints
+
+def hf_encodec_to_reference(hf_state_dict: tp.Dict[str, torch.Tensor], hf_config) -> tp.Tuple[dict, dict]:
+    """Translate a `transformers.EncodecModel` checkpoint (what the reference loads for `facebook/encodec_*` through
+    `HFEncodecCompressionModel`, audiocraft/models/encodec.py:119-121, 323-392) into the reference's own state_dict layout +
+    hyper-parameters.  HF's implementation is the same algorithm with renamed modules
+    (transformers/models/encodec/modeling_encodec.py), so the converted weights run on the kernels unchanged."""
+    c = hf_config
+    if getattr(c, 'norm_type', 'weight_norm') != 'weight_norm':
+        raise NotImplementedError(f"HF EnCodec norm_type '{c.norm_type}' is not built (only weight_norm)")
+    if getattr(c, 'chunk_length_s', None):
+        raise NotImplementedError("chunked HF EnCodec (48 kHz) is not built")
+    hop = int(math.prod(c.upsampling_ratios))
+    frame_rate = math.ceil(c.sampling_rate / hop)
+    n_qs = [int(bw * 1000 // (frame_rate * math.log2(c.codebook_size))) for bw in c.target_bandwidths]
+    cfg = dict(channels=c.audio_channels, dimension=c.hidden_size, n_filters=c.num_filters,
+               n_residual_layers=c.num_residual_layers, ratios=list(c.upsampling_ratios), kernel_size=c.kernel_size,
+               last_kernel_size=c.last_kernel_size, residual_kernel_size=c.residual_kernel_size,
+               dilation_base=c.dilation_growth_rate, causal=c.use_causal_conv, pad_mode=c.pad_mode, compress=c.compress,
+               lstm=c.num_lstm_layers, norm='weight_norm', trim_right_ratio=c.trim_right_ratio,
+               sample_rate=c.sampling_rate, n_q=max(n_qs), bins=c.codebook_size, renormalize=c.normalize,
+               true_skip=not c.use_conv_shortcut, possible_num_codebooks=n_qs)
+    plan = encodec_layers(cfg)
+    kinds = {}
+    for layer in plan['encoder'] + plan['decoder']:
+        side, _, idx = layer['prefix'].split('.')[:3]
+        kinds[(side, idx)] = layer['kind']
+    sd = {}
+    for k, v in hf_state_dict.items():
+        parts = k.split('.')
+        if parts[0] in ('encoder', 'decoder'):
+            side, idx = parts[0], parts[2]
+            rest = '.'.join(parts[3:])
+            rest = rest.replace('parametrizations.weight.original0', 'weight_g').replace('parametrizations.weight.original1', 'weight_v')
+            if rest.startswith('lstm.'):
+                sd[f'{side}.model.{idx}.{rest}'] = v
+            elif rest.startswith(('block.', 'shortcut.')):
+                head, tail = rest.split('.conv.', 1)
+                sd[f'{side}.model.{idx}.{head}.conv.conv.{tail}'] = v
+            else:  # rest = 'conv.<param>'
+                tail = rest.split('conv.', 1)[1]
+                inner = 'convtr.convtr' if kinds.get((side, idx)) == 'convtr' else 'conv.conv'
+                sd[f'{side}.model.{idx}.{inner}.{tail}'] = v
+        elif parts[0] == 'quantizer':
+            sd[f'quantizer.vq.layers.{parts[2]}._codebook.{parts[4]}'] = v
+    return sd, cfg
+
+
+class HFEncodecCompressionModel(EncodecModel):
+    """`facebook/encodec_*` checkpoints on the B200 kernels: same surface as the reference's wrapper
+    (audiocraft/models/encodec.py:323-392), incl. the restriction of `set_num_codebooks` to the bandwidths the
+    checkpoint declares."""
+
+    def __init__(self, hf_state_dict, hf_config, device='cuda', **kw):
+        sd, cfg = hf_encodec_to_reference(hf_state_dict, hf_config)
+        super().__init__(sd, cfg, device, **kw)
+        self.possible_num_codebooks = cfg['possible_num_codebooks']
+        self.set_num_codebooks(max(self.possible_num_codebooks))
+
+    @property
+    def frame_rate(self):
+        return self._frame_rate
+
+    def set_num_codebooks(self, n: int):
+        if n not in self.possible_num_codebooks:
+            raise ValueError(f"Allowed values for num codebooks: {self.possible_num_codebooks}")
+        self.n_q = n
+
+    @staticmethod
+    def from_pretrained_dir(path: str, device='cuda'):
+        """A local snapshot of an HF EnCodec repo (config.json + weights); the hub itself is unreachable offline."""
+        from transformers import EncodecModel as _HF
+        m = _HF.from_pretrained(path, local_files_only=True)
+        return HFEncodecCompressionModel(m.state_dict(), m.config, device)

@@ -56,7 +56,7 @@ def encodec_layers(cfg: dict) -> tp.Dict[str, tp.List[dict]]:
     """Ordered layer plan of the SEANet encoder and decoder with the reference module indices
     (audiocraft/modules/seanet.py:113-150, 207-254).  Each entry:
       kind 'conv'  : prefix, cin, cout, k, stride, dilation, elu (ELU before), res ('in' saves the skip,
-                     'out' adds it)
+                     'out' adds it, 'shortcut' = the 1x1 conv that produces the skip when true_skip is off)
       kind 'convtr': prefix, cin, cout, k, stride, elu
       kind 'lstm'  : prefix, dim, layers
     """
@@ -65,10 +65,15 @@ def encodec_layers(cfg: dict) -> tp.Dict[str, tp.List[dict]]:
 
     def res_entries(prefix, c, j):
         hid = c // cfg['compress']
-        return [dict(kind='conv', prefix=f'{prefix}block.1.conv.conv.', cin=c, cout=hid, k=rk, stride=1,
+        out = []
+        if not cfg.get('true_skip', True):   # SEANetResnetBlock with a 1x1 conv shortcut (seanet.py:54-57)
+            out.append(dict(kind='conv', prefix=f'{prefix}shortcut.conv.conv.', cin=c, cout=c, k=1, stride=1,
+                            dilation=1, elu=False, res='shortcut'))
+        out += [dict(kind='conv', prefix=f'{prefix}block.1.conv.conv.', cin=c, cout=hid, k=rk, stride=1,
                      dilation=cfg['dilation_base'] ** j, elu=True, res='in'),
                 dict(kind='conv', prefix=f'{prefix}block.3.conv.conv.', cin=hid, cout=c, k=1, stride=1,
                      dilation=1, elu=True, res='out')]
+        return out
 
     enc: tp.List[dict] = []
     i, mult = 0, 1

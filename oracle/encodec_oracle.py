@@ -136,6 +136,9 @@ def _resblock(x, sd, prefix, cfg, dilation):
     w2, b2 = _conv_weight(sd, prefix + 'block.3.conv.conv.')
     y = sconv1d(elu(x), w1, b1, dilation=dilation, causal=cfg['causal'], pad_mode=cfg['pad_mode'])
     y = sconv1d(elu(y), w2, b2, causal=cfg['causal'], pad_mode=cfg['pad_mode'])
+    if not cfg.get('true_skip', True):   # 1x1 conv shortcut instead of the identity (seanet.py:54-57)
+        ws, bs = _conv_weight(sd, prefix + 'shortcut.conv.conv.')
+        x = sconv1d(x, ws, bs, causal=cfg['causal'], pad_mode=cfg['pad_mode'])
     return x + y
 
 

@@ -257,3 +257,38 @@ def test_tensor_core_encoder_mode(name):
     first = neq.int().cumsum(1).eq(1) & neq
     assert (margins[first].abs() < 5e-3).all()
     assert (codes.cpu() == g['codes']).float().mean() > 0.98
+
+
+@pytest.mark.parametrize('shortcut', [False, True])
+def test_hf_encodec_checkpoint_on_kernels(shortcut):
+    """an HF-format EnCodec checkpoint (random init here) converted and run on the kernels vs
+    transformers' own CPU implementation; exercises the conv-shortcut residual block and n_q = 32."""
+    import warnings
+    from transformers import EncodecConfig, EncodecModel as HFModel
+    from audiocraft_b200.encodec import HFEncodecCompressionModel, hf_encodec_to_reference
+    warnings.filterwarnings('ignore')
+    hc = EncodecConfig(use_conv_shortcut=shortcut)
+    torch.manual_seed(0)
+    hf = HFModel(hc).eval()
+    hsd = hf.state_dict()
+    g = torch.Generator().manual_seed(1)
+    for k in hsd:
+        if k.endswith('codebook.embed'):
+            hsd[k].copy_(torch.randn(hsd[k].shape, generator=g) * 0.5)
+    x = torch.randn(2, 1, 5000, generator=g) * 0.3
+    with torch.no_grad():
+        enc = hf.encode(x, None, 24.0)
+        dec = hf.decode(enc[0], enc[1])[0]
+    m = HFEncodecCompressionModel(hsd, hc)
+    assert m.sample_rate == 24000 and m.cardinality == 1024 and m.num_codebooks == 32 and m.total_codebooks == 32
+    codes, scale = m.encode(x)
+    sd, cfg = hf_encodec_to_reference(hsd, hc)
+    lat = EO.EncodecOracle(sd, cfg).encode_latent(x)
+    _, margins = EO.rvq_encode(lat, EO.codebooks_of(sd, 32), return_margin=True)
+    _codes_match(codes.cpu(), enc[0][0], margins, f'hf encodec shortcut={shortcut}')
+    torch.testing.assert_close(m.decode(enc[0][0].cuda()).cpu(), dec, rtol=0, atol=1e-4)
+    m.set_num_codebooks(8)
+    c8, _ = m.encode(x)
+    assert c8.shape[1] == 8
+    with pytest.raises(ValueError):
+        m.set_num_codebooks(5)

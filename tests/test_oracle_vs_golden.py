@@ -132,3 +132,32 @@ def test_padding_rules():
         for causal, ratio in [(False, 1.0), (True, 1.0), (True, 0.5), (True, 0.0)]:
             y = EO.sconvtr1d(torch.randn(1, 2, 13), torch.randn(2, 3, k), torch.zeros(3), s, causal, ratio)
             assert y.shape[-1] == 13 * s
+
+
+@pytest.mark.parametrize('shortcut', [False, True])
+def test_oracle_matches_huggingface_encodec(shortcut):
+    """Third-party arithmetic at the boundary: `facebook/encodec_*` goes through
+    transformers.EncodecModel (audiocraft/models/encodec.py:119-121).  transformers is in the image, so HF's own CPU
+    implementation (random init; no checkpoints offline) pins the oracle a second time, through the key conversion."""
+    import warnings
+    from transformers import EncodecConfig, EncodecModel
+    from audiocraft_b200.encodec import hf_encodec_to_reference
+    warnings.filterwarnings('ignore')
+    hc = EncodecConfig(use_conv_shortcut=shortcut)
+    torch.manual_seed(0)
+    m = EncodecModel(hc).eval()
+    hsd = m.state_dict()
+    g = torch.Generator().manual_seed(1)
+    for k in hsd:
+        if k.endswith('codebook.embed'):
+            hsd[k].copy_(torch.randn(hsd[k].shape, generator=g) * 0.5)
+    sd, cfg = hf_encodec_to_reference(hsd, hc)
+    assert cfg['possible_num_codebooks'] == [2, 4, 8, 16, 32] and cfg['true_skip'] == (not shortcut)
+    x = torch.randn(2, 1, 3000, generator=g) * 0.3
+    with torch.no_grad():
+        enc = m.encode(x, None, 24.0)
+        dec = m.decode(enc[0], enc[1])[0]
+    o = EO.EncodecOracle(sd, cfg)
+    codes, scale = o.encode(x)
+    assert scale is None and torch.equal(codes, enc[0][0])
+    torch.testing.assert_close(o.decode(codes), dec, rtol=0, atol=2e-6)
