@@ -107,3 +107,19 @@ def load_musicgen(name: str, device=None, seed: int = 0):
         cm = load_compression_model(os.path.join(name, 'compression_state_dict.bin'), device)
         return MusicGen(name, cm, lm, max_duration=30)
     raise FileNotFoundError(f"MusicGen '{name}': pass a local checkpoint directory or 'synthetic/<small|medium|large>'")
+
+
+def load_audiogen(name: str, device=None, seed: int = 0):
+    """`synthetic/audiogen-medium` (seeded random weights of the released architecture) or a local checkpoint directory."""
+    from .musicgen import AudioGen
+    device = 'cuda' if device is None else device
+    if name.startswith('synthetic/'):
+        scale = name.split('/', 1)[1].replace('audiogen-', '')
+        lm = load_lm_model(f'synthetic/{scale}', device, seed)
+        cm = load_compression_model('synthetic/encodec_16k', device, seed + 1)
+        return AudioGen(name, cm, lm, max_duration=10)
+    if os.path.isdir(name):
+        lm = load_lm_model(os.path.join(name, 'state_dict.bin'), device)
+        cm = load_compression_model(os.path.join(name, 'compression_state_dict.bin'), device)
+        return AudioGen(name, cm, lm, max_duration=10)
+    raise FileNotFoundError(f"AudioGen '{name}': pass a local checkpoint directory or 'synthetic/audiogen-medium'")

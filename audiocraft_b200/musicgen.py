@@ -189,3 +189,33 @@ class MusicGen(BaseGenModel):
 
     def generate_with_chroma(self, *args, **kwargs):
         raise NotImplementedError("melody (chroma) conditioning is not built on the B200 path (SURVEY.md 8f.3)")
+
+
+class AudioGen(BaseGenModel):
+    """audiocraft/models/audiogen.py:23-93: the same LM decode + EnCodec decode path at 16 kHz (codec
+    `encodec_large_nq4_s320`, 4 codebooks, delays [0,1,2,3]); only the defaults differ from MusicGen."""
+
+    def __init__(self, name: str, compression_model: CompressionModel, lm: LMModel,
+                 max_duration: tp.Optional[float] = None):
+        super().__init__(name, compression_model, lm, max_duration)
+        self.set_generation_params(duration=5)  # default duration
+
+    @staticmethod
+    def get_pretrained(name: str = 'facebook/audiogen-medium', device=None):
+        from .loaders import load_audiogen
+        return load_audiogen(name, device=device)
+
+    def set_generation_params(self, use_sampling: bool = True, top_k: int = 250, top_p: float = 0.0,
+                              temperature: float = 1.0, duration: float = 10.0, cfg_coef: float = 3.0,
+                              two_step_cfg: bool = False, extend_stride: float = 2):
+        assert extend_stride < self.max_duration, "Cannot stride by more than max generation duration."
+        self.extend_stride = extend_stride
+        self.duration = duration
+        self.generation_params = {
+            'use_sampling': use_sampling,
+            'temp': temperature,
+            'top_k': top_k,
+            'top_p': top_p,
+            'cfg_coef': cfg_coef,
+            'two_step_cfg': two_step_cfg,
+        }

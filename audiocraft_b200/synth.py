@@ -24,6 +24,12 @@ ENCODEC_CONFIGS: tp.Dict[str, dict] = {
                         causal=False, pad_mode='reflect', compress=2, lstm=2, norm='weight_norm',
                         trim_right_ratio=1.0, sample_rate=32000, n_q=4, bins=2048, renormalize=False,
                         latent_sigma=0.35),
+    # AudioGen's codec (config/model/encodec/encodec_large_nq4_s320.yaml): 16 kHz, hop 320 (50 Hz), 4 x 2048 codes.
+    'encodec_16k': dict(channels=1, dimension=128, n_filters=64, n_residual_layers=1, ratios=[8, 5, 4, 2],
+                        kernel_size=7, last_kernel_size=7, residual_kernel_size=3, dilation_base=2,
+                        causal=False, pad_mode='reflect', compress=2, lstm=2, norm='weight_norm',
+                        trim_right_ratio=1.0, sample_rate=16000, n_q=4, bins=2048, renormalize=False,
+                        latent_sigma=0.35),
     # AudioCraft base 24 kHz causal codec (BASELINE config 1), hop 320 (75 Hz).
     'encodec_24k': dict(channels=1, dimension=128, n_filters=32, n_residual_layers=1, ratios=[8, 5, 4, 2],
                         kernel_size=7, last_kernel_size=7, residual_kernel_size=3, dilation_base=2,

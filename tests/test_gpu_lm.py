@@ -248,3 +248,15 @@ def test_released_widths_match_oracle(name, B):
     torch.testing.assert_close(lg, ref, rtol=2e-2, atol=3e-2)
     out = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=True, top_k=250, cross_attention_src=cross)
     assert out.shape == (B, 4, T) and int(out.min()) >= 0 and int(out.max()) < cfg['card']
+
+
+def test_audiogen_api():
+    """AudioGen rides on the same kernels: 16 kHz codec, 50 Hz frames, its own defaults."""
+    from audiocraft_b200.loaders import load_compression_model, load_lm_model
+    from audiocraft_b200.musicgen import AudioGen
+    ag = AudioGen('debug', load_compression_model('synthetic/encodec_16k'), load_lm_model('synthetic/lm_mini'), max_duration=10)
+    assert ag.sample_rate == 16000 and ag.frame_rate == 50 and ag.duration == 5 and ag.extend_stride == 2
+    ag.set_generation_params(duration=1.0)
+    wav, tok = ag.generate(['dog barking', 'rain'], return_tokens=True)
+    assert tok.shape == (2, 4, 50) and wav.shape == (2, 1, 16000)
+    assert 'cfg_coef_beta' not in ag.generation_params
