@@ -103,7 +103,7 @@ def test_lstm_matches_oracle(hidden, batch, T, layers):
     ref = EO.lstm_block(x, sd, 'l.', layers)
     m = EncodecModel.__new__(EncodecModel)  # only the LSTM launcher is exercised
     from audiocraft_b200 import _lib
-    m._lib, m.device, m.launches = _lib.lib(), torch.device('cuda'), 0
+    m._lib, m.device, m.launches, m._lstm_prec = _lib.lib(), torch.device('cuda'), 0, 0
     layer = m._prepare(dict(kind='lstm', prefix='l.', dim=hidden, layers=layers), sd)
     y = m._lstm(_dev(x), layer)
     torch.testing.assert_close(y.cpu(), ref, rtol=1e-4, atol=2e-5)
