@@ -20,6 +20,7 @@
 #include <math.h>
 #include <new>
 #include <vector>
+#include <utility>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -86,7 +87,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict__ emb, const float* __restrict__ inv_freq,
                                                        const int64_t* __restrict__ seq, const int* __restrict__ P,
                                                        float* __restrict__ x, int d, int n_q, int card, int max_seq,
-                                                       int batch, float pos_scale) {
+                                                       int batch, float pos_scale, float* __restrict__ stats) {
     pdl_trigger();
     pdl_wait();
     const int r = blockIdx.x, b = r % batch, pos = P[0];
@@ -97,13 +98,18 @@ __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict_
     }
     __syncthreads();
     const int half_d = d >> 1;
-    for (int i = threadIdx.x; i < d; i += 256) {
+    for (int i = threadIdx.x; i < d; i += 256) {   // d % 32 == 0: a warp is entirely inside or outside the row
         float v = 0.f;
         for (int k = 0; k < n_q; ++k) v += __half2float(emb[((size_t)k * (card + 1) + tok[k]) * d + i]);
         const int j = i < half_d ? i : i - half_d;
         const float phase = (float)pos / inv_freq[j];
         v += pos_scale * (i < half_d ? cosf(phase) : sinf(phase));
         x[(size_t)r * d + i] = v;
+        if (stats) {   // per 32-feature tile: (sum, centred sum of squares) for the LayerNorm of the first consumer
+            const float sm = warp_sum(v), dv = v - sm * (1.f / 32.f), m2 = warp_sum(dv * dv);
+            if ((threadIdx.x & 31) == 0)
+                *reinterpret_cast<float2*>(stats + ((size_t)(i >> 5) * gridDim.x + r) * 2) = make_float2(sm, m2);
+        }
     }
 }
 
@@ -277,6 +283,285 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
             const int which = n / p.d, nn = n % p.d, h = nn >> 6, dd = nn & 63;
             __half* cache = which ? p.vc : p.kc;
             cache[(((size_t)r * p.H + h) * p.cache_len + tc) * 64 + dd] = __float2half_rn(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ wide skinny GEMM
+// Second-generation decode GEMM (the default step, "v6").  What changed against lm_gemm_kernel and why:
+//   * activations are the A operand (16 rows = one m16 tile), weights the B operand, so a CTA owns 8*FG output features
+//     (FG = 4: 32) and every activation fragment a warp loads is reused for FG feature groups: activation traffic out
+//     of L2 is 16/(8*FG) of the weight bytes instead of equal to them (the 16-feature tile re-read the activations once
+//     per tile: measured L2->SM traffic was 2x the HBM traffic, and the LTS cap is only ~2x HBM bandwidth).
+//   * split-K partial sums never go to global memory: the K-slices of one feature tile form a thread-block CLUSTER, the
+//     non-leader CTAs push their 16 x 32 partial tile into the leader's shared memory (st.shared::cluster), one cluster
+//     barrier, and the leader reduces in a fixed order (bit-reproducible) and runs the epilogue.
+//   * the residual add and LayerNorm are folded into the GEMMs on either side: a producer (WEPI_RESID) writes
+//     x += y and per-(tile,row) statistics (sum, centred sum of squares); a consumer (LNIN) merges those 48 tile
+//     statistics per row (Chan's formula: no E[x^2]-mean^2 cancellation) and normalises the fp32 residual stream while
+//     loading its A fragments.  The three LayerNorm kernels per layer disappear: 8 dependent kernels per layer, not 11.
+enum { WEPI_RESID = 0, WEPI_QKV = 1, WEPI_GELU = 2, WEPI_F32 = 3 };
+
+struct WGemmParams {
+    const __half* W;           // [N][K] fp16, reference layout
+    const __half* X16;         // !LNIN: A operand [>= rows][K] fp16
+    const float* X32;          // LNIN: residual stream [rows][K] fp32 (K == model dim), normalised on load
+    const float* gamma; const float* beta; const float* stats_in; int stat_tiles; float stat_w;
+    int N, K, rows, kslice, nsplit;
+    float* x; float* stats_out;                                                  // RESID (ld = N)
+    float* out_f32; int ld_out;                                                  // F32
+    __half* out_f16;                                                             // GELU (ld = ld_out)
+    float* q32; __half* kc; __half* vc; int d, H, cache_len; const int* pos;     // QKV
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+__device__ __forceinline__ void st_cluster_f32(uint32_t local_smem_addr, uint32_t cta_rank, float v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(cta_rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// shared-memory layout, shared by the kernel and the host-side size computation
+struct WSmem { int pitch, bar, gb, mr, red, recv, total; };
+__host__ __device__ inline WSmem wgemm_smem(int MT, int FG, bool lnin, int kslice, int nsplit) {
+    const int R = 16 * MT, FT = 8 * FG;
+    WSmem L;
+    L.pitch = kslice * 2 + 64;                       // = 64 mod 128: conflict-free 128-bit fragment reads
+    L.bar = FT * L.pitch;
+    L.gb = L.bar + 16;                               // gamma[kslice], beta[kslice]
+    L.mr = L.gb + (lnin ? kslice * 8 : 0);           // (mean, rstd) per row
+    L.red = L.mr + (lnin ? R * 8 : 0);               // [4 warps][R][FT + 1]
+    L.recv = L.red + 4 * R * (FT + 1) * 4;           // [nsplit - 1][R][FT]: partial tiles pushed by the other K-slices
+    L.total = L.recv + (nsplit - 1) * R * FT * 4;
+    return L;
+}
+
+template <int MT, int FG, bool LNIN, int EPI>
+__global__ void __launch_bounds__(128) lm_wgemm_kernel(WGemmParams p) {
+    constexpr int R = 16 * MT, FT = 8 * FG, RP = FT + 1;
+    constexpr int U = LNIN ? (MT == 1 ? 4 : (MT == 2 ? 2 : 1)) : (MT == 1 ? 6 : (MT == 2 ? 3 : 2));
+    extern __shared__ __align__(128) unsigned char gsm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c4 = lane & 3;
+    const int f0 = blockIdx.x * FT;
+    const uint32_t rank = cluster_ctarank();         // == blockIdx.y: the grid is (tiles, nsplit), the cluster (1, nsplit, 1)
+    const int k0 = (int)blockIdx.y * p.kslice;
+    const int ks = p.kslice;                          // K % (32 * nsplit) == 0: every slice is full
+    const WSmem L = wgemm_smem(MT, FG, LNIN, ks, p.nsplit);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + L.bar);
+    float* gbs = reinterpret_cast<float*>(gsm + L.gb);
+    float* mr = reinterpret_cast<float*>(gsm + L.mr);
+    float* red = reinterpret_cast<float*>(gsm + L.red);
+    float* recv = reinterpret_cast<float*>(gsm + L.recv);
+
+    // ---- prologue that does not depend on the previous kernel: weight slab (TMA), gamma/beta
+    const int nfeat = min(FT, p.N - f0);
+    static_assert(EPI != WEPI_RESID || FG == 4, "the residual epilogue needs a 32-feature tile (one warp per row)");
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (p.nsplit > 1) cluster_arrive();              // "this CTA runs": its shared memory may be written by its peers
+    if (warp == 0) {
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)nfeat * (uint32_t)ks * 2u);
+        __syncwarp();
+        if (lane < nfeat) bulk_g2s(gsm + lane * L.pitch, p.W + (size_t)(f0 + lane) * p.K + k0, (uint32_t)ks * 2u, bar);
+    }
+    if constexpr (LNIN) {
+        for (int i = tid; i < (ks >> 2); i += 128) {
+            reinterpret_cast<float4*>(gbs)[i] = reinterpret_cast<const float4*>(p.gamma + k0)[i];
+            reinterpret_cast<float4*>(gbs + ks)[i] = reinterpret_cast<const float4*>(p.beta + k0)[i];
+        }
+    }
+    pdl_trigger();
+    pdl_wait();   // x / activations / statistics written by the previous kernels are visible from here on
+
+    // ---- LayerNorm statistics of every row from the producer's per-tile (sum, M2)
+    if constexpr (LNIN) {
+        const int sub = tid & 7;
+        const float inv_k = 1.f / (float)p.K;
+#pragma unroll
+        for (int pass = 0; pass < MT; ++pass) {
+            const int row = pass * 16 + (tid >> 3);
+            const bool live = row < p.rows;
+            float sm = 0.f;
+            if (live)
+                for (int t = sub; t < p.stat_tiles; t += 8) sm += p.stats_in[((size_t)t * p.rows + row) * 2];
+            sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+            sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+            sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+            const float mean = sm * inv_k;
+            float m2 = 0.f;
+            if (live)
+                for (int t = sub; t < p.stat_tiles; t += 8) {
+                    const float2 st = *reinterpret_cast<const float2*>(p.stats_in + ((size_t)t * p.rows + row) * 2);
+                    const float dm = st.x / p.stat_w - mean;
+                    m2 += st.y + p.stat_w * dm * dm;
+                }
+            m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+            if (sub == 0) { mr[row * 2] = mean; mr[row * 2 + 1] = 1.f / sqrtf(m2 * inv_k + 1e-5f); }
+        }
+        __syncthreads();   // also orders the gamma/beta staging
+    }
+    float mean_a[MT], rstd_a[MT], mean_b[MT], rstd_b[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        if constexpr (LNIN) {
+            mean_a[mt] = mr[(16 * mt + g) * 2]; rstd_a[mt] = mr[(16 * mt + g) * 2 + 1];
+            mean_b[mt] = mr[(16 * mt + g + 8) * 2]; rstd_b[mt] = mr[(16 * mt + g + 8) * 2 + 1];
+        } else {
+            mean_a[mt] = rstd_a[mt] = mean_b[mt] = rstd_b[mt] = 0.f;
+        }
+    }
+
+    float c[MT][FG][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int fg = 0; fg < FG; ++fg) c[mt][fg][0] = c[mt][fg][1] = c[mt][fg][2] = c[mt][fg][3] = 0.f;
+
+    // ---- main loop: warp w reduces over k-blocks [kb0, kb1) of the slice, all FG feature groups
+    const int nkb = ks >> 5;
+    const int kbw = (nkb + 3) >> 2;
+    const int kb0 = min(nkb, warp * kbw), kb1 = min(nkb, kb0 + kbw);
+    const unsigned char* wrow = gsm + g * L.pitch + 16 * c4;
+    bool w_ready = false;
+    for (int kb = kb0; kb < kb1; kb += U) {
+        float4 xa[LNIN ? U : 1][MT][2], xb[LNIN ? U : 1][MT][2];
+        uint4 ha[LNIN ? 1 : U][MT], hb[LNIN ? 1 : U][MT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool kv = kb + u < kb1;
+            const size_t kk = (size_t)k0 + (size_t)(kb + u) * 32 + 8 * c4;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int ra = 16 * mt + g, rb = ra + 8;
+                if constexpr (LNIN) {
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4* pa = reinterpret_cast<const float4*>(p.X32 + (size_t)ra * p.K + kk);
+                    const float4* pb = reinterpret_cast<const float4*>(p.X32 + (size_t)rb * p.K + kk);
+                    const bool la = kv && ra < p.rows, lb = kv && rb < p.rows;
+                    xa[u][mt][0] = la ? pa[0] : z; xa[u][mt][1] = la ? pa[1] : z;
+                    xb[u][mt][0] = lb ? pb[0] : z; xb[u][mt][1] = lb ? pb[1] : z;
+                } else {
+                    const uint4 z = make_uint4(0, 0, 0, 0);
+                    ha[u][mt] = (kv && ra < p.rows) ? *reinterpret_cast<const uint4*>(p.X16 + (size_t)ra * p.K + kk) : z;
+                    hb[u][mt] = (kv && rb < p.rows) ? *reinterpret_cast<const uint4*>(p.X16 + (size_t)rb * p.K + kk) : z;
+                }
+            }
+        }
+        if (!w_ready) { mbar_wait(bar, 0); w_ready = true; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (kb + u < kb1) {
+                uint4 qa[MT], qb[MT];
+                if constexpr (LNIN) {
+                    const int kl = (kb + u) * 32 + 8 * c4;   // index into the staged gamma / beta slice
+                    const float4 g0 = *reinterpret_cast<const float4*>(gbs + kl), g1 = *reinterpret_cast<const float4*>(gbs + kl + 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(gbs + ks + kl), b1 = *reinterpret_cast<const float4*>(gbs + ks + kl + 4);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const float4 a0 = xa[u][mt][0], a1 = xa[u][mt][1], e0 = xb[u][mt][0], e1 = xb[u][mt][1];
+                        const float ma = mean_a[mt], sa = rstd_a[mt], mb = mean_b[mt], sb = rstd_b[mt];
+                        qa[mt].x = pack_h2((a0.x - ma) * sa * g0.x + b0.x, (a0.y - ma) * sa * g0.y + b0.y);
+                        qa[mt].y = pack_h2((a0.z - ma) * sa * g0.z + b0.z, (a0.w - ma) * sa * g0.w + b0.w);
+                        qa[mt].z = pack_h2((a1.x - ma) * sa * g1.x + b1.x, (a1.y - ma) * sa * g1.y + b1.y);
+                        qa[mt].w = pack_h2((a1.z - ma) * sa * g1.z + b1.z, (a1.w - ma) * sa * g1.w + b1.w);
+                        qb[mt].x = pack_h2((e0.x - mb) * sb * g0.x + b0.x, (e0.y - mb) * sb * g0.y + b0.y);
+                        qb[mt].y = pack_h2((e0.z - mb) * sb * g0.z + b0.z, (e0.w - mb) * sb * g0.w + b0.w);
+                        qb[mt].z = pack_h2((e1.x - mb) * sb * g1.x + b1.x, (e1.y - mb) * sb * g1.y + b1.y);
+                        qb[mt].w = pack_h2((e1.z - mb) * sb * g1.z + b1.z, (e1.w - mb) * sb * g1.w + b1.w);
+                        if (16 * mt + g >= p.rows) qa[mt] = make_uint4(0, 0, 0, 0);
+                        if (16 * mt + g + 8 >= p.rows) qb[mt] = make_uint4(0, 0, 0, 0);
+                    }
+                } else {
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) { qa[mt] = ha[u][mt]; qb[mt] = hb[u][mt]; }
+                }
+#pragma unroll
+                for (int fg = 0; fg < FG; ++fg) {
+                    // 8 consecutive k of feature fg*8+g: k-pairs P0..P3; the same k permutation as the A rows
+                    const uint4 wv = *reinterpret_cast<const uint4*>(wrow + (size_t)fg * 8 * L.pitch + (kb + u) * 64);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma16816(c[mt][fg], qa[mt].x, qb[mt].x, qa[mt].y, qb[mt].y, wv.x, wv.y);
+                        mma16816(c[mt][fg], qa[mt].z, qb[mt].z, qa[mt].w, qb[mt].w, wv.z, wv.w);
+                    }
+                }
+            }
+        }
+    }
+    if (!w_ready) mbar_wait(bar, 0);   // never leave with a bulk copy in flight
+
+    // ---- K reduction: 4 warps of the CTA (fixed order), then the K-slices of the cluster (fixed order)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int fg = 0; fg < FG; ++fg) {
+            float* r0 = red + ((size_t)warp * R + 16 * mt + g) * RP + fg * 8 + 2 * c4;
+            r0[0] = c[mt][fg][0]; r0[1] = c[mt][fg][1];
+            r0[8 * RP] = c[mt][fg][2]; r0[8 * RP + 1] = c[mt][fg][3];
+        }
+    __syncthreads();
+    constexpr int EPT = R * FT / 128;                 // tile elements per thread
+    float v[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        const int idx = tid + 128 * j, row = idx / FT, feat = idx % FT;
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) a += red[((size_t)w * R + row) * RP + feat];
+        v[j] = a;
+    }
+    if (p.nsplit > 1) {
+        cluster_wait();                                // every CTA of the cluster has started
+        if (rank != 0) {
+#pragma unroll
+            for (int j = 0; j < EPT; ++j)
+                st_cluster_f32(smem_u32(recv + ((size_t)(rank - 1) * R * FT) + tid + 128 * j), 0u, v[j]);
+        }
+        cluster_sync_all();                            // release the pushes / acquire them in the leader
+        if (rank != 0) return;
+        for (int s = 0; s < p.nsplit - 1; ++s)
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) v[j] += recv[(size_t)s * R * FT + tid + 128 * j];
+    }
+
+    // ---- epilogue (leader CTA of the tile)
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        const int idx = tid + 128 * j, row = idx / FT, feat = idx % FT, n = f0 + feat;
+        if constexpr (EPI == WEPI_RESID) {
+            // FT == 32: a warp holds the 32 features of one row.  x += y, and the tile's LayerNorm statistics.
+            if (row < p.rows) {   // warp-uniform
+                float* xp = p.x + (size_t)row * p.N + n;
+                const float xn = *xp + v[j];
+                *xp = xn;
+                const float sm = warp_sum(xn), dv = xn - sm * (1.f / 32.f), m2 = warp_sum(dv * dv);
+                if (lane == 0)
+                    *reinterpret_cast<float2*>(p.stats_out + ((size_t)blockIdx.x * p.rows + row) * 2) = make_float2(sm, m2);
+            }
+        } else {
+            if (row >= p.rows || n >= p.N) continue;
+            if (EPI == WEPI_F32) {
+                p.out_f32[(size_t)row * p.ld_out + n] = v[j];
+            } else if (EPI == WEPI_GELU) {
+                p.out_f16[(size_t)row * p.ld_out + n] = __float2half_rn(gelu_erf(half_round(v[j])));
+            } else {  // WEPI_QKV
+                if (n < p.d) {
+                    p.q32[(size_t)row * p.d + n] = v[j];
+                } else {
+                    const int which = (n - p.d) / p.d, nn = n % p.d, h = nn >> 6, dd = nn & 63;
+                    __half* cache = which ? p.vc : p.kc;
+                    cache[(((size_t)row * p.H + h) * p.cache_len + p.pos[0]) * 64 + dd] = __float2half_rn(v[j]);
+                }
+            }
         }
     }
 }
@@ -853,6 +1138,7 @@ struct acb_lm {
     int launches = 0;
     bool has_cross = false;
     bool pdl = true;          // programmatic dependent launch between the kernels of a step
+    bool wide = true;         // v6 step (wide cluster GEMMs, LayerNorm folded in); ACB_LM_STEP=v5 selects the round-1 kernels
     bool chain = false;       // GEMM/LN phases between attention kernels run in persistent chain kernels (opt-in)
     int chain_grid = 0, chain_slab = 0;
     size_t chain_smem = 0;
@@ -1086,7 +1372,8 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
 
     if (!gemms_only) {
         ACB_LAUNCH(lm_embed_kernel, dim3(rows), dim3(256), 0, s, pdl, (const __half*)lm->w.emb, lm->w.inv_freq,
-                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale);
+                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale,
+                   (float*)nullptr);
         ++nl;
         DBG("lm_embed_kernel", -1);
     }
@@ -1180,6 +1467,187 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
     return ACB_OK;
 }
 
+// ---- v6 step: wide GEMMs with cluster split-K and LayerNorm folded into producer / consumer (8 kernels per layer)
+struct WTile { int fg, ns, kslice; };
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+// Tile plan of one GEMM: 32 features per CTA (16 when N is not a multiple of 32), and K cut into `ns` cluster slices
+// until the slab fits ACB_LM_SLAB_KB (default 56 KB: three CTAs per SM stay co-resident, which is what lets the next
+// kernel's weight prefetch overlap under PDL) and the grid covers ACB_LM_FILL % of the SMs (default 90).
+static WTile pick_wtile(int N, int K, int sms, bool need32) {
+    WTile t;
+    t.fg = (N % 32 == 0 || need32) ? 4 : 2;
+    const int ft = 8 * t.fg, tiles = acb_ceil_div(N, ft), nkb = K / 32;
+    const int slab_cap = env_int("ACB_LM_SLAB_KB", 56) * 1024, fill = env_int("ACB_LM_FILL", 90);
+    int ns = 1;
+    while (ns < 8 && nkb % (2 * ns) == 0 && nkb / (2 * ns) >= 2 &&
+           ((size_t)ft * (K / ns) * 2 > (size_t)slab_cap || tiles * ns * 100 < sms * fill))
+        ns *= 2;
+    t.ns = ns;
+    t.kslice = K / ns;
+    return t;
+}
+
+template <int MT, int FG, bool LNIN, int EPI>
+static cudaError_t wgemm_launch_one(const WGemmParams& p, cudaStream_t s, bool pdl) {
+    const WSmem L = wgemm_smem(MT, FG, LNIN, p.kslice, p.nsplit);
+    static int attr_done = 0;   // per instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(lm_wgemm_kernel<MT, FG, LNIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(lm_wgemm_kernel<MT, FG, LNIN, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return e;
+        attr_done = 1;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(acb_ceil_div(p.N, 8 * FG), p.nsplit);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = (size_t)L.total;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (p.nsplit > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = (unsigned)p.nsplit; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, lm_wgemm_kernel<MT, FG, LNIN, EPI>, p);
+}
+template <int FG, bool LNIN, int EPI>
+static cudaError_t wgemm_launch_mt(int mt, const WGemmParams& p, cudaStream_t s, bool pdl) {
+    switch (mt) {
+        case 1: return wgemm_launch_one<1, FG, LNIN, EPI>(p, s, pdl);
+        case 2: return wgemm_launch_one<2, FG, LNIN, EPI>(p, s, pdl);
+        default: return wgemm_launch_one<4, FG, LNIN, EPI>(p, s, pdl);
+    }
+}
+template <bool LNIN, int EPI>
+static int wgemm_launch(int mt, int fg, const WGemmParams& p, cudaStream_t s, bool pdl) {
+    ACB_REQUIRE(wgemm_smem(mt, fg, LNIN, p.kslice, p.nsplit).total <= 200 * 1024,
+                "lm_wgemm: tile needs more than 200 KB of shared memory (N=%d K=%d kslice=%d)", p.N, p.K, p.kslice);
+    if (fg == 4) ACB_CHECK_CUDA((wgemm_launch_mt<4, LNIN, EPI>(mt, p, s, pdl)));
+    else {
+        if constexpr (EPI == WEPI_RESID) { acb_set_error("lm_wgemm: residual tiles must be 32 features wide"); return ACB_ERR_INVALID; }
+        else ACB_CHECK_CUDA((wgemm_launch_mt<2, LNIN, EPI>(mt, p, s, pdl)));
+    }
+    return ACB_OK;
+}
+
+static int mt_for_rows(int rows) { return rows <= 16 ? 1 : (rows <= 32 ? 2 : 4); }
+
+// embed(+stats) | L x [QKV(LN1) | attn | O(+x,stats) | CQ(LNc) | cross-attn | CO(+x,stats) | FFN1(LN2,GELU) | FFN2(+x,stats)]
+// | heads(LNout) | sample.   Statistics live in buffers.part ([d/32 tiles][rows][2] floats); cross queries reuse q32.
+static int enqueue_step_wide(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only, bool capturing) {
+    const acb_lm_config& c = lm->cfg;
+    const acb_lm_buffers& B = lm->buf;
+    const int d = c.dim, ffn = c.ffn_dim, L = c.num_layers, H = c.num_heads, rows = lm->rows, mt = mt_for_rows(rows);
+    const size_t kv_layer = (size_t)c.max_rows * H * c.max_seq * 64;
+    const size_t ckv_layer = (size_t)c.max_rows * H * c.max_text * 64;
+    const float scale = 1.0f / sqrtf(64.f);
+    const bool pdl = lm->pdl;
+    float* stats = B.part;
+    int nl = 0;
+
+    auto base = [&](const void* W, int N, int K, bool need32) {
+        WGemmParams p{};
+        const WTile t = pick_wtile(N, K, lm->sms, need32);
+        p.W = (const __half*)W; p.N = N; p.K = K; p.rows = rows; p.kslice = t.kslice; p.nsplit = t.ns;
+        p.d = d; p.H = H;
+        return std::make_pair(p, t.fg);
+    };
+    auto with_ln = [&](WGemmParams& p, const float* gamma, const float* beta) {
+        p.X32 = B.x; p.gamma = gamma; p.beta = beta; p.stats_in = stats; p.stat_tiles = d / 32; p.stat_w = 32.f;
+    };
+    auto resid = [&](const void* W, const void* X16, int K, const char* what, int layer) -> int {
+        auto [p, fg] = base(W, d, K, true);
+        p.X16 = (const __half*)X16; p.x = B.x; p.stats_out = stats;
+        ACB_TRY((wgemm_launch<false, WEPI_RESID>(mt, fg, p, s, pdl)));
+        ++nl;
+        DBG(what, layer);
+        return ACB_OK;
+    };
+
+    if (!gemms_only) {
+        ACB_LAUNCH(lm_embed_kernel, dim3(rows), dim3(256), 0, s, pdl, (const __half*)lm->w.emb, lm->w.inv_freq,
+                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale, stats);
+        ++nl;
+        DBG("lm_embed_kernel", -1);
+    }
+    for (int l = 0; l < L; ++l) {
+        const float* ln = lm->w.ln + (size_t)l * 6 * d;
+        {   // --- self attention
+            auto [p, fg] = base((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, 3 * d, d, false);
+            with_ln(p, ln, ln + d);
+            p.q32 = B.q32; p.kc = (__half*)B.k_cache + l * kv_layer; p.vc = (__half*)B.v_cache + l * kv_layer;
+            p.cache_len = c.max_seq; p.pos = B.pos;
+            ACB_TRY((wgemm_launch<true, WEPI_QKV>(mt, fg, p, s, pdl))); ++nl;
+            DBG("wgemm_QKV", l);
+        }
+        if (!gemms_only) {
+            AttnParams a{B.q32, 1, 0, (__half*)B.k_cache + l * kv_layer, (__half*)B.v_cache + l * kv_layer, (__half*)B.a16,
+                         H, d, c.max_seq, B.pos, 0, scale};
+            ACB_LAUNCH(lm_attn_kernel, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            ++nl;
+            DBG("lm_attn_kernel", l);
+        }
+        ACB_TRY(resid((const __half*)lm->w.w_o + (size_t)l * d * d, B.a16, d, "wgemm_O", l));
+        if (lm->has_cross) {   // --- cross attention
+            {
+                auto [p, fg] = base((const __half*)lm->w.w_cq + (size_t)l * d * d, d, d, false);
+                with_ln(p, ln + 2 * d, ln + 3 * d);
+                p.out_f32 = B.q32; p.ld_out = d;
+                ACB_TRY((wgemm_launch<true, WEPI_F32>(mt, fg, p, s, pdl))); ++nl;
+                DBG("wgemm_CQ", l);
+            }
+            if (!gemms_only) {
+                AttnParams a{B.q32, 1, 0, (__half*)B.ck_cache + l * ckv_layer, (__half*)B.cv_cache + l * ckv_layer,
+                             (__half*)B.a16, H, d, c.max_text, B.pos, lm->text_len, scale};
+                ACB_LAUNCH(lm_cross_attn_kernel, dim3(acb_ceil_div(rows * H, 8)), dim3(256), 0, s, pdl, a, rows);
+                ++nl;
+                DBG("lm_cross_attn_kernel", l);
+            }
+            ACB_TRY(resid((const __half*)lm->w.w_co + (size_t)l * d * d, B.a16, d, "wgemm_CO", l));
+        }
+        {   // --- feed forward
+            auto [p, fg] = base((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, ffn, d, false);
+            with_ln(p, ln + 4 * d, ln + 5 * d);
+            p.out_f16 = (__half*)B.f16; p.ld_out = ffn;
+            ACB_TRY((wgemm_launch<true, WEPI_GELU>(mt, fg, p, s, pdl))); ++nl;
+            DBG("wgemm_FFN1", l);
+        }
+        ACB_TRY(resid((const __half*)lm->w.w_ff2 + (size_t)l * d * ffn, B.f16, ffn, "wgemm_FFN2", l));
+    }
+    {
+        const int N = c.n_q * c.card;
+        auto [p, fg] = base(lm->w.heads, N, d, false);
+        with_ln(p, lm->w.out_norm, lm->w.out_norm + d);
+        p.out_f32 = B.logits; p.ld_out = N;
+        ACB_TRY((wgemm_launch<true, WEPI_F32>(mt, fg, p, s, pdl))); ++nl;
+        DBG("wgemm_heads", -1);
+    }
+    if (!gemms_only) {
+        int NP = 1;
+        while (NP < c.card) NP <<= 1;
+        SampleParams sp{B.logits, lm->samp.noise_from_buffer ? B.noise : nullptr, logits_out, B.seq, B.seq_mask, B.pos,
+                        c.max_seq, nullptr, lm->batch, rows, c.n_q, c.card, NP, lm->samp.use_sampling, lm->samp.top_k,
+                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0};
+        size_t smem = ((size_t)c.card + 2 * (size_t)NP) * sizeof(float);
+        ACB_LAUNCH(lm_sample_kernel, dim3(c.n_q, lm->batch), dim3(1024), smem, s, pdl, sp);
+        ++nl;
+        DBG("lm_sample_kernel", -1);
+    }
+    if (n_launch) *n_launch = nl;
+    return ACB_OK;
+}
+
 // Decode step with chain kernels: embed | chain0 | L x [attn | chainX | cross-attn | chainY] | sample.
 static int enqueue_step_chain(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool chains_only, bool capturing) {
     const acb_lm_config& c = lm->cfg;
@@ -1195,7 +1663,8 @@ static int enqueue_step_chain(acb_lm* lm, cudaStream_t s, float* logits_out, int
     ACB_CHECK_CUDA(cudaMemsetAsync(B.plan, 0, lm->chain_off.size() * sizeof(unsigned), s));
     if (!chains_only) {
         ACB_LAUNCH(lm_embed_kernel, dim3(rows), dim3(256), 0, s, false, (const __half*)lm->w.emb, lm->w.inv_freq,
-                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale);
+                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale,
+                   (float*)nullptr);
         ++nl;
         DBG("lm_embed_kernel", -1);
     }
@@ -1242,8 +1711,9 @@ static int enqueue_step_chain(acb_lm* lm, cudaStream_t s, float* logits_out, int
 
 static int enqueue_step(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only = false,
                         bool capturing = false) {
-    return lm->chain ? enqueue_step_chain(lm, s, logits_out, n_launch, gemms_only, capturing)
-                     : enqueue_step_kernels(lm, s, logits_out, n_launch, gemms_only, capturing);
+    if (lm->chain) return enqueue_step_chain(lm, s, logits_out, n_launch, gemms_only, capturing);
+    return lm->wide ? enqueue_step_wide(lm, s, logits_out, n_launch, gemms_only, capturing)
+                    : enqueue_step_kernels(lm, s, logits_out, n_launch, gemms_only, capturing);
 }
 
 extern "C" int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, const acb_lm_buffers* buf, acb_lm_t** out) {
@@ -1350,6 +1820,8 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
         lm->pdl = !(e && e[0] == '1');
         // persistent chain kernels are an opt-in experiment: measured SLOWER than one kernel per phase on B200
         // (profiles/r1_perf_step_v5_chain_slower.log, r1_ncu_chain_kernel_raw.csv), see DESIGN.md section 3.1
+        const char* ev = getenv("ACB_LM_STEP");
+        lm->wide = !(ev && ev[0] == 'v' && ev[1] == '5');
         const char* ec = getenv("ACB_LM_CHAIN");
         lm->chain = (ec && ec[0] == '1') && lm->buf.plan != nullptr;
         if (lm->chain) ACB_TRY(build_chain_plan(lm, s));

@@ -298,6 +298,7 @@ class LMModel:
             samp = _lib.LMSampling(0, 1.0, 0, 0.0, float(cfg_coef), 0, 0)
             _lib.check(self._lib.acb_lm_begin(self._handle, _lib.ptr(cross), B, rows, text_len, S, C.byref(samp),
                                               _lib.stream()), 'lm_begin')
+            self.launches_per_step = self._lib.acb_lm_launches_per_step(self._handle)
             n = S - 1 if n_steps is None else n_steps
             out = torch.empty((n, B, K, self.card), device=self.device, dtype=torch.float32)
             for i in range(n):
