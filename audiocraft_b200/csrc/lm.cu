@@ -306,7 +306,7 @@ struct WGemmParams {
     const __half* W;           // [N][K] fp16, reference layout
     const __half* X16;         // !LNIN: A operand [>= rows][K] fp16
     const float* X32;          // LNIN: residual stream [rows][K] fp32 (K == model dim), normalised on load
-    const float* gamma; const float* beta; const float* stats_in; int stat_tiles; float stat_w;
+    const float* gamma; const float* beta; const float* stats_in; int stat_tiles; float stat_w, inv_stat_w, inv_k;
     int N, K, rows, kslice, nsplit;
     float* x; float* stats_out;                                                  // RESID (ld = N)
     float* out_f32; int ld_out;                                                  // F32
@@ -329,30 +329,62 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 
 // shared-memory layout, shared by the kernel and the host-side size computation
-struct WSmem { int pitch, bar, gb, mr, red, recv, total; };
+constexpr int WG_WARPS = 8, WG_THREADS = WG_WARPS * 32, WG_MAX_STAT = 8;   // statistics tiles per lane: d <= 2048
+struct WSmem { int pitch_w, bar, gb, mr, red, recv, total; };
 __host__ __device__ inline WSmem wgemm_smem(int MT, int FG, bool lnin, int kslice, int nsplit) {
     const int R = 16 * MT, FT = 8 * FG;
     WSmem L;
-    L.pitch = kslice * 2 + 64;                       // = 64 mod 128: conflict-free 128-bit fragment reads
-    L.bar = FT * L.pitch;
-    L.gb = L.bar + 16;                               // gamma[kslice], beta[kslice]
-    L.mr = L.gb + (lnin ? kslice * 8 : 0);           // (mean, rstd) per row
-    L.red = L.mr + (lnin ? R * 8 : 0);               // [4 warps][R][FT + 1]
-    L.recv = L.red + 4 * R * (FT + 1) * 4;           // [nsplit - 1][R][FT]: partial tiles pushed by the other K-slices
+    L.pitch_w = kslice * 2 + 64;                       // = 64 mod 128 when kslice % 64 == 0: conflict-free 128-bit reads
+    L.bar = FT * L.pitch_w;
+    L.gb = L.bar + 16;                                 // gamma[kslice], beta[kslice]
+    L.mr = L.gb + (lnin ? kslice * 8 : 0);             // (mean, rstd) per row
+    L.red = L.mr + (lnin ? R * 8 : 0);                 // [warps][R][FT + 1]
+    L.recv = L.red + WG_WARPS * R * (FT + 1) * 4;      // [nsplit - 1][R][FT]: partial tiles pushed by the other K-slices
     L.total = L.recv + (nsplit - 1) * R * FT * 4;
     return L;
 }
 
+// One k-block (32 reduction indices) of the A operand as this lane holds it: rows g and g+8 of every 16-row tile,
+// 8 consecutive k each -- raw fp32 residual values (normalised when consumed) or fp16 activations.
+template <int MT, bool LNIN> struct WFrag;
+template <int MT> struct WFrag<MT, true> { float4 a[MT][2], b[MT][2]; };
+template <int MT> struct WFrag<MT, false> { uint4 a[MT], b[MT]; };
+
+// The lane's row pointers (rows g and g+8 of every tile, at its first k); null for rows that do not exist.
+template <int MT> struct WRows { const unsigned char* a[MT]; const unsigned char* b[MT]; };
+
+template <int MT, bool LNIN>
+__device__ __forceinline__ void wfrag_load(WFrag<MT, LNIN>& f, const WRows<MT>& rp, int byte_off) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        if constexpr (LNIN) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            f.a[mt][0] = rp.a[mt] ? *reinterpret_cast<const float4*>(rp.a[mt] + byte_off) : z;
+            f.a[mt][1] = rp.a[mt] ? *reinterpret_cast<const float4*>(rp.a[mt] + byte_off + 16) : z;
+            f.b[mt][0] = rp.b[mt] ? *reinterpret_cast<const float4*>(rp.b[mt] + byte_off) : z;
+            f.b[mt][1] = rp.b[mt] ? *reinterpret_cast<const float4*>(rp.b[mt] + byte_off + 16) : z;
+        } else {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            f.a[mt] = rp.a[mt] ? *reinterpret_cast<const uint4*>(rp.a[mt] + byte_off) : z;
+            f.b[mt] = rp.b[mt] ? *reinterpret_cast<const uint4*>(rp.b[mt] + byte_off) : z;
+        }
+    }
+}
+
+// Code size matters here: a decode GEMM runs for ~3 us, and every instruction line is fetched once per launch like
+// data (the first version of this kernel, with the LayerNorm arithmetic unrolled over four k-blocks in flight, was
+// 2 760 instructions = 44 KB and took ~5 us longer per launch than the 430-instruction round-1 kernel).  So the k-loop
+// is ONE compact body (`#pragma unroll 1`), software-pipelined by hand: the next k-block's activations are requested
+// before the current one is normalised and multiplied; 8 warps split the K-slice so each runs only 2-3 iterations.
 template <int MT, int FG, bool LNIN, int EPI>
-__global__ void __launch_bounds__(128) lm_wgemm_kernel(WGemmParams p) {
+__global__ void __launch_bounds__(WG_THREADS) lm_wgemm_kernel(WGemmParams p) {
     constexpr int R = 16 * MT, FT = 8 * FG, RP = FT + 1;
-    constexpr int U = LNIN ? (MT == 1 ? 4 : (MT == 2 ? 2 : 1)) : (MT == 1 ? 6 : (MT == 2 ? 3 : 2));
+    static_assert(EPI != WEPI_RESID || FG == 4, "the residual epilogue needs a 32-feature tile (one warp per row)");
     extern __shared__ __align__(128) unsigned char gsm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c4 = lane & 3;
     const int f0 = blockIdx.x * FT;
     const uint32_t rank = cluster_ctarank();         // == blockIdx.y: the grid is (tiles, nsplit), the cluster (1, nsplit, 1)
-    const int k0 = (int)blockIdx.y * p.kslice;
-    const int ks = p.kslice;                          // K % (32 * nsplit) == 0: every slice is full
+    const int ks = p.kslice, k0 = (int)blockIdx.y * ks;   // K % (32 * nsplit) == 0: every slice is full
     const WSmem L = wgemm_smem(MT, FG, LNIN, ks, p.nsplit);
     uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + L.bar);
     float* gbs = reinterpret_cast<float*>(gsm + L.gb);
@@ -361,18 +393,18 @@ __global__ void __launch_bounds__(128) lm_wgemm_kernel(WGemmParams p) {
     float* recv = reinterpret_cast<float*>(gsm + L.recv);
 
     // ---- prologue that does not depend on the previous kernel: weight slab (TMA), gamma/beta
-    const int nfeat = min(FT, p.N - f0);
-    static_assert(EPI != WEPI_RESID || FG == 4, "the residual epilogue needs a 32-feature tile (one warp per row)");
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (p.nsplit > 1) cluster_arrive();              // "this CTA runs": its shared memory may be written by its peers
     if (warp == 0) {
+        const int nfeat = min(FT, p.N - f0);
         if (lane == 0) mbar_expect_tx(bar, (uint32_t)nfeat * (uint32_t)ks * 2u);
         __syncwarp();
-        if (lane < nfeat) bulk_g2s(gsm + lane * L.pitch, p.W + (size_t)(f0 + lane) * p.K + k0, (uint32_t)ks * 2u, bar);
+        if (lane < nfeat) bulk_g2s(gsm + lane * L.pitch_w, p.W + (size_t)(f0 + lane) * p.K + k0, (uint32_t)ks * 2u, bar);
     }
     if constexpr (LNIN) {
-        for (int i = tid; i < (ks >> 2); i += 128) {
+#pragma unroll 1
+        for (int i = tid; i < (ks >> 2); i += WG_THREADS) {
             reinterpret_cast<float4*>(gbs)[i] = reinterpret_cast<const float4*>(p.gamma + k0)[i];
             reinterpret_cast<float4*>(gbs + ks)[i] = reinterpret_cast<const float4*>(p.beta + k0)[i];
         }
@@ -380,34 +412,55 @@ __global__ void __launch_bounds__(128) lm_wgemm_kernel(WGemmParams p) {
     pdl_trigger();
     pdl_wait();   // x / activations / statistics written by the previous kernels are visible from here on
 
-    // ---- LayerNorm statistics of every row from the producer's per-tile (sum, M2)
+    // warp w reduces over k-blocks [kb0, kb1) of the slice; its first activations are requested before anything else
+    const int nkb = ks >> 5;
+    const int kbw = (nkb + WG_WARPS - 1) / WG_WARPS;
+    const int kb0 = min(nkb, warp * kbw), kb1 = min(nkb, kb0 + kbw);
+    constexpr int ESZ = LNIN ? 4 : 2;                // bytes per activation element
+    WRows<MT> rp;
+    {
+        const unsigned char* xbase = LNIN ? reinterpret_cast<const unsigned char*>(p.X32) : reinterpret_cast<const unsigned char*>(p.X16);
+        xbase += ((size_t)g * p.K + k0 + 8 * c4) * ESZ;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            rp.a[mt] = 16 * mt + g < p.rows ? xbase + (size_t)(16 * mt) * p.K * ESZ : nullptr;
+            rp.b[mt] = 16 * mt + g + 8 < p.rows ? xbase + (size_t)(16 * mt + 8) * p.K * ESZ : nullptr;
+        }
+    }
+    WFrag<MT, LNIN> cur, nxt;
+    if (kb0 < kb1) wfrag_load<MT, LNIN>(cur, rp, kb0 * 32 * ESZ);
+
+    // ---- LayerNorm statistics of every row from the producer's per-tile (sum, M2): 8 lanes per row, one pass
     if constexpr (LNIN) {
         const int sub = tid & 7;
-        const float inv_k = 1.f / (float)p.K;
-#pragma unroll
-        for (int pass = 0; pass < MT; ++pass) {
-            const int row = pass * 16 + (tid >> 3);
-            const bool live = row < p.rows;
+        const float inv_k = p.inv_k, inv_w = p.inv_stat_w;
+#pragma unroll 1
+        for (int row = tid >> 3; row < R; row += WG_THREADS / 8) {   // warp-uniform trip count
+            const float2* st = reinterpret_cast<const float2*>(p.stats_in) + row;
+            float2 sv[WG_MAX_STAT];
             float sm = 0.f;
-            if (live)
-                for (int t = sub; t < p.stat_tiles; t += 8) sm += p.stats_in[((size_t)t * p.rows + row) * 2];
+#pragma unroll
+            for (int i = 0; i < WG_MAX_STAT; ++i) {
+                const int t = sub + 8 * i;
+                sv[i] = (row < p.rows && t < p.stat_tiles) ? st[(size_t)t * p.rows] : make_float2(0.f, 0.f);
+                sm += sv[i].x;
+            }
             sm += __shfl_xor_sync(0xffffffffu, sm, 4);
             sm += __shfl_xor_sync(0xffffffffu, sm, 2);
             sm += __shfl_xor_sync(0xffffffffu, sm, 1);
             const float mean = sm * inv_k;
             float m2 = 0.f;
-            if (live)
-                for (int t = sub; t < p.stat_tiles; t += 8) {
-                    const float2 st = *reinterpret_cast<const float2*>(p.stats_in + ((size_t)t * p.rows + row) * 2);
-                    const float dm = st.x / p.stat_w - mean;
-                    m2 += st.y + p.stat_w * dm * dm;
-                }
+#pragma unroll
+            for (int i = 0; i < WG_MAX_STAT; ++i) {
+                const float dm = sv[i].x * inv_w - mean;
+                if (sub + 8 * i < p.stat_tiles) m2 += sv[i].y + p.stat_w * dm * dm;
+            }
             m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
             m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
             m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
-            if (sub == 0) { mr[row * 2] = mean; mr[row * 2 + 1] = 1.f / sqrtf(m2 * inv_k + 1e-5f); }
+            if (sub == 0) { mr[row * 2] = mean; mr[row * 2 + 1] = rsqrtf(m2 * inv_k + 1e-5f); }
         }
-        __syncthreads();   // also orders the gamma/beta staging
+        __syncthreads();   // mr and the gamma/beta staging
     }
     float mean_a[MT], rstd_a[MT], mean_b[MT], rstd_b[MT];
 #pragma unroll
@@ -426,97 +479,67 @@ __global__ void __launch_bounds__(128) lm_wgemm_kernel(WGemmParams p) {
 #pragma unroll
         for (int fg = 0; fg < FG; ++fg) c[mt][fg][0] = c[mt][fg][1] = c[mt][fg][2] = c[mt][fg][3] = 0.f;
 
-    // ---- main loop: warp w reduces over k-blocks [kb0, kb1) of the slice, all FG feature groups
-    const int nkb = ks >> 5;
-    const int kbw = (nkb + 3) >> 2;
-    const int kb0 = min(nkb, warp * kbw), kb1 = min(nkb, kb0 + kbw);
-    const unsigned char* wrow = gsm + g * L.pitch + 16 * c4;
-    bool w_ready = false;
-    for (int kb = kb0; kb < kb1; kb += U) {
-        float4 xa[LNIN ? U : 1][MT][2], xb[LNIN ? U : 1][MT][2];
-        uint4 ha[LNIN ? 1 : U][MT], hb[LNIN ? 1 : U][MT];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const bool kv = kb + u < kb1;
-            const size_t kk = (size_t)k0 + (size_t)(kb + u) * 32 + 8 * c4;
+    mbar_wait(bar, 0);   // the weight slab has landed (every thread waits: never leave with a bulk copy in flight)
+    const unsigned char* wrow = gsm + g * L.pitch_w + 16 * c4;
+#pragma unroll 1
+    for (int kb = kb0; kb < kb1; ++kb) {
+        if (kb + 1 < kb1) wfrag_load<MT, LNIN>(nxt, rp, (kb + 1) * 32 * ESZ);
+        uint4 qa[MT], qb[MT];
+        if constexpr (LNIN) {
+            const int kl = kb * 32 + 8 * c4;   // first of this lane's 8 consecutive k inside the slice
+            const float4 g0 = *reinterpret_cast<const float4*>(gbs + kl), g1 = *reinterpret_cast<const float4*>(gbs + kl + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(gbs + ks + kl), b1 = *reinterpret_cast<const float4*>(gbs + ks + kl + 4);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const int ra = 16 * mt + g, rb = ra + 8;
-                if constexpr (LNIN) {
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4* pa = reinterpret_cast<const float4*>(p.X32 + (size_t)ra * p.K + kk);
-                    const float4* pb = reinterpret_cast<const float4*>(p.X32 + (size_t)rb * p.K + kk);
-                    const bool la = kv && ra < p.rows, lb = kv && rb < p.rows;
-                    xa[u][mt][0] = la ? pa[0] : z; xa[u][mt][1] = la ? pa[1] : z;
-                    xb[u][mt][0] = lb ? pb[0] : z; xb[u][mt][1] = lb ? pb[1] : z;
-                } else {
-                    const uint4 z = make_uint4(0, 0, 0, 0);
-                    ha[u][mt] = (kv && ra < p.rows) ? *reinterpret_cast<const uint4*>(p.X16 + (size_t)ra * p.K + kk) : z;
-                    hb[u][mt] = (kv && rb < p.rows) ? *reinterpret_cast<const uint4*>(p.X16 + (size_t)rb * p.K + kk) : z;
-                }
+                const float4 a0 = cur.a[mt][0], a1 = cur.a[mt][1], e0 = cur.b[mt][0], e1 = cur.b[mt][1];
+                const float ma = mean_a[mt], sa = rstd_a[mt], mb = mean_b[mt], sb = rstd_b[mt];
+                qa[mt].x = pack_h2((a0.x - ma) * sa * g0.x + b0.x, (a0.y - ma) * sa * g0.y + b0.y);
+                qa[mt].y = pack_h2((a0.z - ma) * sa * g0.z + b0.z, (a0.w - ma) * sa * g0.w + b0.w);
+                qa[mt].z = pack_h2((a1.x - ma) * sa * g1.x + b1.x, (a1.y - ma) * sa * g1.y + b1.y);
+                qa[mt].w = pack_h2((a1.z - ma) * sa * g1.z + b1.z, (a1.w - ma) * sa * g1.w + b1.w);
+                qb[mt].x = pack_h2((e0.x - mb) * sb * g0.x + b0.x, (e0.y - mb) * sb * g0.y + b0.y);
+                qb[mt].y = pack_h2((e0.z - mb) * sb * g0.z + b0.z, (e0.w - mb) * sb * g0.w + b0.w);
+                qb[mt].z = pack_h2((e1.x - mb) * sb * g1.x + b1.x, (e1.y - mb) * sb * g1.y + b1.y);
+                qb[mt].w = pack_h2((e1.z - mb) * sb * g1.z + b1.z, (e1.w - mb) * sb * g1.w + b1.w);
+                // (rows >= p.rows were loaded as zeros and normalise to finite values that only reach output rows the
+                //  epilogue never stores)
+            }
+        } else {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) { qa[mt] = cur.a[mt]; qb[mt] = cur.b[mt]; }
+        }
+#pragma unroll
+        for (int fg = 0; fg < FG; ++fg) {
+            // 8 consecutive k of feature fg*8+g: k-pairs P0..P3; the same k permutation as the A rows
+            const uint4 wv = *reinterpret_cast<const uint4*>(wrow + fg * 8 * L.pitch_w + kb * 64);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                mma16816(c[mt][fg], qa[mt].x, qb[mt].x, qa[mt].y, qb[mt].y, wv.x, wv.y);
+                mma16816(c[mt][fg], qa[mt].z, qb[mt].z, qa[mt].w, qb[mt].w, wv.z, wv.w);
             }
         }
-        if (!w_ready) { mbar_wait(bar, 0); w_ready = true; }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (kb + u < kb1) {
-                uint4 qa[MT], qb[MT];
-                if constexpr (LNIN) {
-                    const int kl = (kb + u) * 32 + 8 * c4;   // index into the staged gamma / beta slice
-                    const float4 g0 = *reinterpret_cast<const float4*>(gbs + kl), g1 = *reinterpret_cast<const float4*>(gbs + kl + 4);
-                    const float4 b0 = *reinterpret_cast<const float4*>(gbs + ks + kl), b1 = *reinterpret_cast<const float4*>(gbs + ks + kl + 4);
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const float4 a0 = xa[u][mt][0], a1 = xa[u][mt][1], e0 = xb[u][mt][0], e1 = xb[u][mt][1];
-                        const float ma = mean_a[mt], sa = rstd_a[mt], mb = mean_b[mt], sb = rstd_b[mt];
-                        qa[mt].x = pack_h2((a0.x - ma) * sa * g0.x + b0.x, (a0.y - ma) * sa * g0.y + b0.y);
-                        qa[mt].y = pack_h2((a0.z - ma) * sa * g0.z + b0.z, (a0.w - ma) * sa * g0.w + b0.w);
-                        qa[mt].z = pack_h2((a1.x - ma) * sa * g1.x + b1.x, (a1.y - ma) * sa * g1.y + b1.y);
-                        qa[mt].w = pack_h2((a1.z - ma) * sa * g1.z + b1.z, (a1.w - ma) * sa * g1.w + b1.w);
-                        qb[mt].x = pack_h2((e0.x - mb) * sb * g0.x + b0.x, (e0.y - mb) * sb * g0.y + b0.y);
-                        qb[mt].y = pack_h2((e0.z - mb) * sb * g0.z + b0.z, (e0.w - mb) * sb * g0.w + b0.w);
-                        qb[mt].z = pack_h2((e1.x - mb) * sb * g1.x + b1.x, (e1.y - mb) * sb * g1.y + b1.y);
-                        qb[mt].w = pack_h2((e1.z - mb) * sb * g1.z + b1.z, (e1.w - mb) * sb * g1.w + b1.w);
-                        if (16 * mt + g >= p.rows) qa[mt] = make_uint4(0, 0, 0, 0);
-                        if (16 * mt + g + 8 >= p.rows) qb[mt] = make_uint4(0, 0, 0, 0);
-                    }
-                } else {
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) { qa[mt] = ha[u][mt]; qb[mt] = hb[u][mt]; }
-                }
-#pragma unroll
-                for (int fg = 0; fg < FG; ++fg) {
-                    // 8 consecutive k of feature fg*8+g: k-pairs P0..P3; the same k permutation as the A rows
-                    const uint4 wv = *reinterpret_cast<const uint4*>(wrow + (size_t)fg * 8 * L.pitch + (kb + u) * 64);
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        mma16816(c[mt][fg], qa[mt].x, qb[mt].x, qa[mt].y, qb[mt].y, wv.x, wv.y);
-                        mma16816(c[mt][fg], qa[mt].z, qb[mt].z, qa[mt].w, qb[mt].w, wv.z, wv.w);
-                    }
-                }
-            }
-        }
+        cur = nxt;
     }
-    if (!w_ready) mbar_wait(bar, 0);   // never leave with a bulk copy in flight
 
-    // ---- K reduction: 4 warps of the CTA (fixed order), then the K-slices of the cluster (fixed order)
+    // ---- K reduction: the warps of the CTA (fixed order), then the K-slices of the cluster (fixed order)
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int fg = 0; fg < FG; ++fg) {
-            float* r0 = red + ((size_t)warp * R + 16 * mt + g) * RP + fg * 8 + 2 * c4;
+            float* r0 = red + (warp * R + 16 * mt + g) * RP + fg * 8 + 2 * c4;
             r0[0] = c[mt][fg][0]; r0[1] = c[mt][fg][1];
             r0[8 * RP] = c[mt][fg][2]; r0[8 * RP + 1] = c[mt][fg][3];
         }
     __syncthreads();
-    constexpr int EPT = R * FT / 128;                 // tile elements per thread
+    constexpr int EPT = (R * FT + WG_THREADS - 1) / WG_THREADS;   // tile elements per thread
     float v[EPT];
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-        const int idx = tid + 128 * j, row = idx / FT, feat = idx % FT;
+        const int idx = tid + WG_THREADS * j, row = idx / FT, feat = idx % FT;
         float a = 0.f;
+        if (idx < R * FT)
 #pragma unroll
-        for (int w = 0; w < 4; ++w) a += red[((size_t)w * R + row) * RP + feat];
+            for (int w = 0; w < WG_WARPS; ++w) a += red[(w * R + row) * RP + feat];
         v[j] = a;
     }
     if (p.nsplit > 1) {
@@ -524,22 +547,25 @@ __global__ void __launch_bounds__(128) lm_wgemm_kernel(WGemmParams p) {
         if (rank != 0) {
 #pragma unroll
             for (int j = 0; j < EPT; ++j)
-                st_cluster_f32(smem_u32(recv + ((size_t)(rank - 1) * R * FT) + tid + 128 * j), 0u, v[j]);
+                if (tid + WG_THREADS * j < R * FT)
+                    st_cluster_f32(smem_u32(recv + (rank - 1) * R * FT + tid + WG_THREADS * j), 0u, v[j]);
         }
         cluster_sync_all();                            // release the pushes / acquire them in the leader
         if (rank != 0) return;
+#pragma unroll 1
         for (int s = 0; s < p.nsplit - 1; ++s)
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) v[j] += recv[(size_t)s * R * FT + tid + 128 * j];
+            for (int j = 0; j < EPT; ++j)
+                if (tid + WG_THREADS * j < R * FT) v[j] += recv[s * R * FT + tid + WG_THREADS * j];
     }
 
     // ---- epilogue (leader CTA of the tile)
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-        const int idx = tid + 128 * j, row = idx / FT, feat = idx % FT, n = f0 + feat;
+        const int idx = tid + WG_THREADS * j, row = idx / FT, feat = idx % FT, n = f0 + feat;
         if constexpr (EPI == WEPI_RESID) {
             // FT == 32: a warp holds the 32 features of one row.  x += y, and the tile's LayerNorm statistics.
-            if (row < p.rows) {   // warp-uniform
+            if (row < p.rows) {   // warp-uniform (R * FT is a multiple of WG_THREADS here)
                 float* xp = p.x + (size_t)row * p.N + n;
                 const float xn = *xp + v[j];
                 *xp = xn;
@@ -548,18 +574,18 @@ __global__ void __launch_bounds__(128) lm_wgemm_kernel(WGemmParams p) {
                     *reinterpret_cast<float2*>(p.stats_out + ((size_t)blockIdx.x * p.rows + row) * 2) = make_float2(sm, m2);
             }
         } else {
-            if (row >= p.rows || n >= p.N) continue;
+            if (idx >= R * FT || row >= p.rows || n >= p.N) continue;
             if (EPI == WEPI_F32) {
                 p.out_f32[(size_t)row * p.ld_out + n] = v[j];
             } else if (EPI == WEPI_GELU) {
                 p.out_f16[(size_t)row * p.ld_out + n] = __float2half_rn(gelu_erf(half_round(v[j])));
-            } else {  // WEPI_QKV
-                if (n < p.d) {
-                    p.q32[(size_t)row * p.d + n] = v[j];
+            } else {  // WEPI_QKV: the tile lies inside one of q / k / v and inside one head (FT | 64, d % 64 == 0)
+                const int which = f0 >= 2 * p.d ? 2 : (f0 >= p.d ? 1 : 0), nn = n - which * p.d;
+                if (which == 0) {
+                    p.q32[(size_t)row * p.d + nn] = v[j];
                 } else {
-                    const int which = (n - p.d) / p.d, nn = n % p.d, h = nn >> 6, dd = nn & 63;
-                    __half* cache = which ? p.vc : p.kc;
-                    cache[(((size_t)row * p.H + h) * p.cache_len + p.pos[0]) * 64 + dd] = __float2half_rn(v[j]);
+                    __half* cache = which == 2 ? p.vc : p.kc;
+                    cache[(((size_t)row * p.H + (nn >> 6)) * p.cache_len + p.pos[0]) * 64 + (nn & 63)] = __float2half_rn(v[j]);
                 }
             }
         }
@@ -1503,7 +1529,7 @@ static cudaError_t wgemm_launch_one(const WGemmParams& p, cudaStream_t s, bool p
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(acb_ceil_div(p.N, 8 * FG), p.nsplit);
-    cfg.blockDim = dim3(128);
+    cfg.blockDim = dim3(WG_THREADS);
     cfg.dynamicSmemBytes = (size_t)L.total;
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
@@ -1565,6 +1591,7 @@ static int enqueue_step_wide(acb_lm* lm, cudaStream_t s, float* logits_out, int*
     };
     auto with_ln = [&](WGemmParams& p, const float* gamma, const float* beta) {
         p.X32 = B.x; p.gamma = gamma; p.beta = beta; p.stats_in = stats; p.stat_tiles = d / 32; p.stat_w = 32.f;
+        p.inv_stat_w = 1.f / 32.f; p.inv_k = 1.f / (float)d;
     };
     auto resid = [&](const void* W, const void* X16, int K, const char* what, int layer) -> int {
         auto [p, fg] = base(W, d, K, true);
