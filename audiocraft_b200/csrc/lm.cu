@@ -20,6 +20,7 @@
 #include <math.h>
 #include <new>
 #include <vector>
+#include <algorithm>
 #include <utility>
 #include <stdio.h>
 #include <stdlib.h>
@@ -288,7 +289,8 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ wide skinny GEMM
-// Second-generation decode GEMM (the default step, "v6").  What changed against lm_gemm_kernel and why:
+// Second-generation decode GEMM ("v6", opt-in with ACB_LM_STEP=v6: parity-tested, but measured SLOWER than the default
+// step -- 2.55 vs 2.25 ms at KV 1, see DESIGN.md section 3.1 for the in-kernel time stamps).  What it changes and why:
 //   * activations are the A operand (16 rows = one m16 tile), weights the B operand, so a CTA owns 8*FG output features
 //     (FG = 4: 32) and every activation fragment a warp loads is reused for FG feature groups: activation traffic out
 //     of L2 is 16/(8*FG) of the weight bytes instead of equal to them (the 16-feature tile re-read the activations once
@@ -312,6 +314,7 @@ struct WGemmParams {
     float* out_f32; int ld_out;                                                  // F32
     __half* out_f16;                                                             // GELU (ld = ld_out)
     float* q32; __half* kc; __half* vc; int d, H, cache_len; const int* pos;     // QKV
+    unsigned long long* timing;   // debug (ACB_LM_TIMING=1): per CTA, 8 time stamps of thread 0
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -322,6 +325,14 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t local_smem_addr, uint32_
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(cta_rank));
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+__device__ __forceinline__ void wg_stamp(const WGemmParams& p, int slot) {
+    if (p.timing && threadIdx.x == 0) {
+        unsigned long long t;
+        if (slot == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        else t = (unsigned long long)clock64();
+        p.timing[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    }
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -392,6 +403,7 @@ __global__ void __launch_bounds__(WG_THREADS) lm_wgemm_kernel(WGemmParams p) {
     float* red = reinterpret_cast<float*>(gsm + L.red);
     float* recv = reinterpret_cast<float*>(gsm + L.recv);
 
+    wg_stamp(p, 0); wg_stamp(p, 1);
     // ---- prologue that does not depend on the previous kernel: weight slab (TMA), gamma/beta
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -411,6 +423,7 @@ __global__ void __launch_bounds__(WG_THREADS) lm_wgemm_kernel(WGemmParams p) {
     }
     pdl_trigger();
     pdl_wait();   // x / activations / statistics written by the previous kernels are visible from here on
+    wg_stamp(p, 2);
 
     // warp w reduces over k-blocks [kb0, kb1) of the slice; its first activations are requested before anything else
     const int nkb = ks >> 5;
@@ -479,7 +492,9 @@ __global__ void __launch_bounds__(WG_THREADS) lm_wgemm_kernel(WGemmParams p) {
 #pragma unroll
         for (int fg = 0; fg < FG; ++fg) c[mt][fg][0] = c[mt][fg][1] = c[mt][fg][2] = c[mt][fg][3] = 0.f;
 
+    wg_stamp(p, 3);
     mbar_wait(bar, 0);   // the weight slab has landed (every thread waits: never leave with a bulk copy in flight)
+    wg_stamp(p, 4);
     const unsigned char* wrow = gsm + g * L.pitch_w + 16 * c4;
 #pragma unroll 1
     for (int kb = kb0; kb < kb1; ++kb) {
@@ -521,6 +536,7 @@ __global__ void __launch_bounds__(WG_THREADS) lm_wgemm_kernel(WGemmParams p) {
         cur = nxt;
     }
 
+    wg_stamp(p, 5);
     // ---- K reduction: the warps of the CTA (fixed order), then the K-slices of the cluster (fixed order)
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
@@ -551,6 +567,7 @@ __global__ void __launch_bounds__(WG_THREADS) lm_wgemm_kernel(WGemmParams p) {
                     st_cluster_f32(smem_u32(recv + (rank - 1) * R * FT + tid + WG_THREADS * j), 0u, v[j]);
         }
         cluster_sync_all();                            // release the pushes / acquire them in the leader
+        wg_stamp(p, 6);
         if (rank != 0) return;
 #pragma unroll 1
         for (int s = 0; s < p.nsplit - 1; ++s)
@@ -590,6 +607,7 @@ __global__ void __launch_bounds__(WG_THREADS) lm_wgemm_kernel(WGemmParams p) {
             }
         }
     }
+    wg_stamp(p, 7);
 }
 
 // ------------------------------------------------------------------------------------------------ attention (1 query)
@@ -1164,13 +1182,18 @@ struct acb_lm {
     int launches = 0;
     bool has_cross = false;
     bool pdl = true;          // programmatic dependent launch between the kernels of a step
-    bool wide = true;         // v6 step (wide cluster GEMMs, LayerNorm folded in); ACB_LM_STEP=v5 selects the round-1 kernels
+    bool wide = false;        // ACB_LM_STEP=v6: wide cluster GEMMs with LayerNorm folded in (8 kernels/layer; measured slower)
     bool chain = false;       // GEMM/LN phases between attention kernels run in persistent chain kernels (opt-in)
     int chain_grid = 0, chain_slab = 0;
     size_t chain_smem = 0;
     std::vector<ChainPhase> plan;            // host copy of every chain's phases, in launch order
     std::vector<int> chain_off, chain_len;   // per chain launch: offset / count into plan
+    // ACB_LM_TIMING=1 (debug): in-kernel time stamps of the layer-0 GEMMs of a directly enqueued step
+    unsigned long long* timing = nullptr;
+    struct TimedGemm { const char* what; int ctas; };
+    std::vector<TimedGemm> timed;
 };
+constexpr int ACB_TIMING_MAX_CTAS = 1024, ACB_TIMING_MAX_GEMMS = 8;
 constexpr size_t ACB_PLAN_COUNTER_BYTES = 4096;   // first bytes of buffers.plan: one barrier counter per chain launch
 
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its
@@ -1589,6 +1612,14 @@ static int enqueue_step_wide(acb_lm* lm, cudaStream_t s, float* logits_out, int*
         p.d = d; p.H = H;
         return std::make_pair(p, t.fg);
     };
+    if (lm->timing && !capturing) lm->timed.clear();
+    auto tag = [&](WGemmParams& p, int fg, const char* what, int layer) {   // debug time stamps for the layer-0 GEMMs
+        if (!lm->timing || capturing || layer != 0 || (int)lm->timed.size() >= ACB_TIMING_MAX_GEMMS) return;
+        const int ctas = acb_ceil_div(p.N, 8 * fg) * p.nsplit;
+        if (ctas > ACB_TIMING_MAX_CTAS) return;
+        p.timing = lm->timing + (size_t)lm->timed.size() * ACB_TIMING_MAX_CTAS * 8;
+        lm->timed.push_back({what, ctas});
+    };
     auto with_ln = [&](WGemmParams& p, const float* gamma, const float* beta) {
         p.X32 = B.x; p.gamma = gamma; p.beta = beta; p.stats_in = stats; p.stat_tiles = d / 32; p.stat_w = 32.f;
         p.inv_stat_w = 1.f / 32.f; p.inv_k = 1.f / (float)d;
@@ -1596,6 +1627,7 @@ static int enqueue_step_wide(acb_lm* lm, cudaStream_t s, float* logits_out, int*
     auto resid = [&](const void* W, const void* X16, int K, const char* what, int layer) -> int {
         auto [p, fg] = base(W, d, K, true);
         p.X16 = (const __half*)X16; p.x = B.x; p.stats_out = stats;
+        tag(p, fg, what, layer);
         ACB_TRY((wgemm_launch<false, WEPI_RESID>(mt, fg, p, s, pdl)));
         ++nl;
         DBG(what, layer);
@@ -1615,6 +1647,7 @@ static int enqueue_step_wide(acb_lm* lm, cudaStream_t s, float* logits_out, int*
             with_ln(p, ln, ln + d);
             p.q32 = B.q32; p.kc = (__half*)B.k_cache + l * kv_layer; p.vc = (__half*)B.v_cache + l * kv_layer;
             p.cache_len = c.max_seq; p.pos = B.pos;
+            tag(p, fg, "wgemm_QKV", l);
             ACB_TRY((wgemm_launch<true, WEPI_QKV>(mt, fg, p, s, pdl))); ++nl;
             DBG("wgemm_QKV", l);
         }
@@ -1631,6 +1664,7 @@ static int enqueue_step_wide(acb_lm* lm, cudaStream_t s, float* logits_out, int*
                 auto [p, fg] = base((const __half*)lm->w.w_cq + (size_t)l * d * d, d, d, false);
                 with_ln(p, ln + 2 * d, ln + 3 * d);
                 p.out_f32 = B.q32; p.ld_out = d;
+                tag(p, fg, "wgemm_CQ", l);
                 ACB_TRY((wgemm_launch<true, WEPI_F32>(mt, fg, p, s, pdl))); ++nl;
                 DBG("wgemm_CQ", l);
             }
@@ -1647,6 +1681,7 @@ static int enqueue_step_wide(acb_lm* lm, cudaStream_t s, float* logits_out, int*
             auto [p, fg] = base((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, ffn, d, false);
             with_ln(p, ln + 4 * d, ln + 5 * d);
             p.out_f16 = (__half*)B.f16; p.ld_out = ffn;
+            tag(p, fg, "wgemm_FFN1", l);
             ACB_TRY((wgemm_launch<true, WEPI_GELU>(mt, fg, p, s, pdl))); ++nl;
             DBG("wgemm_FFN1", l);
         }
@@ -1792,6 +1827,7 @@ extern "C" int acb_lm_destroy(acb_lm_t* lm) {
     if (!lm) return ACB_OK;
     drop_graph(lm);
     if (lm->capture_stream) cudaStreamDestroy(lm->capture_stream);
+    if (lm->timing) cudaFree(lm->timing);
     delete lm;
     return ACB_OK;
 }
@@ -1847,8 +1883,12 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
         lm->pdl = !(e && e[0] == '1');
         // persistent chain kernels are an opt-in experiment: measured SLOWER than one kernel per phase on B200
         // (profiles/r1_perf_step_v5_chain_slower.log, r1_ncu_chain_kernel_raw.csv), see DESIGN.md section 3.1
+        if (env_int("ACB_LM_TIMING", 0) && !lm->timing) {
+            ACB_CHECK_CUDA(cudaMalloc(&lm->timing, (size_t)ACB_TIMING_MAX_GEMMS * ACB_TIMING_MAX_CTAS * 64));
+            ACB_CHECK_CUDA(cudaMemset(lm->timing, 0, (size_t)ACB_TIMING_MAX_GEMMS * ACB_TIMING_MAX_CTAS * 64));
+        }
         const char* ev = getenv("ACB_LM_STEP");
-        lm->wide = !(ev && ev[0] == 'v' && ev[1] == '5');
+        lm->wide = ev && ev[0] == 'v' && ev[1] == '6';
         const char* ec = getenv("ACB_LM_CHAIN");
         lm->chain = (ec && ec[0] == '1') && lm->buf.plan != nullptr;
         if (lm->chain) ACB_TRY(build_chain_plan(lm, s));
@@ -1859,6 +1899,21 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
         int rc = enqueue_step(lm, lm->capture_stream, nullptr, &lm->launches, false, true);
         cudaError_t e = cudaStreamEndCapture(lm->capture_stream, &lm->graph);
         if (rc == ACB_OK && e == cudaSuccess) e = cudaGraphInstantiate(&lm->exec, lm->graph, 0);
+        if (rc == ACB_OK && e == cudaSuccess && env_int("ACB_LM_GRAPH_INFO", 0)) {   // how many edges are programmatic (PDL)?
+            size_t ne = 0;
+            if (cudaGraphGetEdges_v2(lm->graph, nullptr, nullptr, nullptr, &ne) == cudaSuccess && ne) {
+                std::vector<cudaGraphNode_t> from(ne), to(ne);
+                std::vector<cudaGraphEdgeData> ed(ne);
+                size_t prog = 0, port_prog = 0;
+                if (cudaGraphGetEdges_v2(lm->graph, from.data(), to.data(), ed.data(), &ne) == cudaSuccess)
+                    for (size_t i = 0; i < ne; ++i) {
+                        prog += ed[i].type == cudaGraphDependencyTypeProgrammatic;
+                        port_prog += ed[i].from_port == cudaGraphKernelNodePortProgrammatic;
+                    }
+                fprintf(stderr, "[acb graph] %zu edges, %zu programmatic (from_port programmatic: %zu), pdl=%d\n", ne, prog, port_prog, (int)lm->pdl);
+            }
+            cudaGetLastError();
+        }
         if (rc == ACB_OK && e == cudaSuccess) return ACB_OK;
         cudaGetLastError();
         drop_graph(lm);
@@ -1880,9 +1935,37 @@ extern "C" int acb_lm_steps(acb_lm_t* lm, int n_steps, void* stream) {
     return ACB_OK;
 }
 
+// Debug report of the in-kernel time stamps (ACB_LM_TIMING=1): per timed GEMM, the spread of CTA start times and the
+// median / max cycles from CTA start to each stamp.
+static int report_timing(acb_lm* lm, cudaStream_t s) {
+    ACB_CHECK_CUDA(cudaStreamSynchronize(s));
+    std::vector<unsigned long long> h((size_t)ACB_TIMING_MAX_CTAS * 8);
+    static const char* names[8] = {"", "start", "pdl_wait", "stats", "slab", "loop", "cluster", "end"};
+    for (size_t gi = 0; gi < lm->timed.size(); ++gi) {
+        const int n = lm->timed[gi].ctas;
+        ACB_CHECK_CUDA(cudaMemcpy(h.data(), lm->timing + gi * ACB_TIMING_MAX_CTAS * 8, (size_t)n * 64, cudaMemcpyDeviceToHost));
+        unsigned long long g0 = ~0ull, g1 = 0;
+        for (int i = 0; i < n; ++i) { g0 = std::min(g0, h[i * 8]); g1 = std::max(g1, h[i * 8]); }
+        fprintf(stderr, "[acb timing] %-11s %4d CTAs, start spread %llu ns;  cycles since CTA start (median/max):", lm->timed[gi].what, n, g1 - g0);
+        for (int sl = 2; sl < 8; ++sl) {
+            std::vector<long long> v;
+            for (int i = 0; i < n; ++i)
+                if (h[i * 8 + sl] > h[i * 8 + 1]) v.push_back((long long)(h[i * 8 + sl] - h[i * 8 + 1]));
+            if (v.empty()) continue;
+            std::sort(v.begin(), v.end());
+            fprintf(stderr, "  %s %lld/%lld", names[sl], v[v.size() / 2], v.back());
+        }
+        fprintf(stderr, "\n");
+    }
+    ACB_CHECK_CUDA(cudaMemset(lm->timing, 0, (size_t)ACB_TIMING_MAX_GEMMS * ACB_TIMING_MAX_CTAS * 64));
+    return ACB_OK;
+}
+
 extern "C" int acb_lm_step_logits(acb_lm_t* lm, float* logits_out, void* stream) {
     ACB_REQUIRE(lm && lm->rows > 0, "acb_lm_step_logits: call acb_lm_begin first");
-    return enqueue_step(lm, (cudaStream_t)stream, logits_out, nullptr);
+    ACB_TRY(enqueue_step(lm, (cudaStream_t)stream, logits_out, nullptr));
+    if (lm->timing && lm->wide && !lm->chain) ACB_TRY(report_timing(lm, (cudaStream_t)stream));
+    return ACB_OK;
 }
 
 extern "C" int acb_lm_debug_gemms(acb_lm_t* lm, void* stream, int* n_launches) {
@@ -1909,4 +1992,54 @@ extern "C" int acb_sample(const float* logits, const float* noise, int64_t* toke
     lm_sample_kernel<<<dim3(n_q, batch), 1024, smem, (cudaStream_t)stream>>>(sp);
     ACB_LAUNCH_CHECK();
     return ACB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ dependency-latency probe
+// A chain of `n_kernels` dependent EMPTY kernels (grid `ctas` x `threads`, `smem` bytes of dynamic shared memory each)
+// captured in one graph -- with programmatic (PDL) edges when pdl != 0 -- and replayed `reps` times: the time per
+// kernel is the floor any decode step of that many dependent kernels can reach on this GPU.  Measurement aid only.
+__global__ void acb_probe_kernel(int* sink) {
+    pdl_trigger();
+    pdl_wait();
+    if (sink && threadIdx.x == 0 && blockIdx.x == 0) sink[0] += 1;   // a dependent read-modify-write through global memory
+}
+
+extern "C" int acb_debug_chain_latency(int n_kernels, int ctas, int threads, int smem, int pdl, int reps, float* us_per_kernel,
+                                       void* scratch) {
+    ACB_REQUIRE(n_kernels >= 1 && n_kernels <= 4096 && ctas >= 1 && threads >= 32 && threads <= 1024 && reps >= 1 && us_per_kernel,
+                "acb_debug_chain_latency: bad argument");
+    ACB_REQUIRE(smem >= 0 && smem <= 200 * 1024, "acb_debug_chain_latency: smem out of range");
+    if (smem > 48 * 1024)
+        ACB_CHECK_CUDA(cudaFuncSetAttribute(acb_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaStream_t s;
+    ACB_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = ACB_OK;
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    for (int i = 0; i < n_kernels && e == cudaSuccess; ++i)
+        e = launch_k(acb_probe_kernel, dim3(ctas), dim3(threads), (size_t)smem, s, pdl != 0, (int*)scratch);
+    cudaError_t e2 = cudaStreamEndCapture(s, &graph);
+    if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) {
+        for (int i = 0; i < 3; ++i) cudaGraphLaunch(exec, s);
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < reps; ++i) cudaGraphLaunch(exec, s);
+        cudaEventRecord(e1, s);
+        e = cudaStreamSynchronize(s);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        *us_per_kernel = ms * 1e3f / (float)reps / (float)n_kernels;
+    }
+    if (e != cudaSuccess) { acb_set_error("acb_debug_chain_latency: %s", cudaGetErrorString(e)); rc = ACB_ERR_CUDA; cudaGetLastError(); }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    cudaStreamDestroy(s);
+    return rc;
 }

@@ -209,6 +209,13 @@ int acb_lm_rows_pad(int rows);
 /* Number of kernel launches one decode step enqueues (bench.py reports gpu_launches from it). */
 int acb_lm_launches_per_step(const acb_lm_t* lm);
 
+/* Measurement aid (no reference counterpart): time per kernel, in microseconds, of a CUDA graph holding a chain of
+ * `n_kernels` dependent empty kernels (grid `ctas` x `threads`, `smem` bytes of dynamic shared memory; programmatic
+ * dependent-launch edges when pdl != 0), replayed `reps` times.  This is the floor for a decode step of that many
+ * dependent kernels.  `scratch`: one device int the kernels increment, or NULL. */
+int acb_debug_chain_latency(int n_kernels, int ctas, int threads, int smem, int pdl, int reps, float* us_per_kernel,
+                            void* scratch);
+
 /* Stand-alone sampler (tail of _sample_next_token, lm.py:403-418; utils/utils.py:88-141) for unit tests:
  * logits [rows][n_q][card] fp32 ([cond; null] rows when rows == 2*batch), noise optional, tokens [batch][n_q]. */
 int acb_sample(const float* logits, const float* noise, int64_t* tokens, int batch, int rows, int n_q, int card,

@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--scale', default='medium')
 ap.add_argument('--batch', type=int, default=8)
 ap.add_argument('--one', type=int, default=-1, help='run a single direct (non-graph) step at this KV length and exit')
+ap.add_argument('--reps', type=int, default=1, help='with --one: repeat the step (ACB_LM_TIMING=1 prints stamps each time)')
 a = ap.parse_args()
 
 lm = load_lm_model(f'synthetic/{a.scale}')
@@ -29,10 +30,11 @@ _lib.check(lm._lib.acb_lm_begin(lm._handle, _lib.ptr(cross), B, 2 * B, 16, S, C.
 pos = lm._bufs['pos']
 kv_tok = 2 * lm.dim * 2 * lm.num_layers
 if a.one >= 0:
-    pos[0] = a.one
-    torch.cuda.synchronize()
-    _lib.check(lm._lib.acb_lm_step_logits(lm._handle, None, _lib.stream()))
-    torch.cuda.synchronize()
+    for _ in range(a.reps):
+        pos[0] = a.one
+        torch.cuda.synchronize()
+        _lib.check(lm._lib.acb_lm_step_logits(lm._handle, None, _lib.stream()))
+        torch.cuda.synchronize()
     sys.exit(0)
 print(f'pdl={lm._lib.acb_lm_uses_pdl(lm._handle)} launches/step={lm._lib.acb_lm_launches_per_step(lm._handle)} '
       f'W_step={lm.weight_bytes_per_step / 1e9:.2f} GB')

@@ -232,27 +232,30 @@ def test_chain_kernel_mode_matches_default(monkeypatch):
 @pytest.mark.parametrize('name,B,env', [('lm_mini', 3, {}), ('lm_medium_2l', 8, {}),
                                         ('lm_medium_2l', 8, {'ACB_LM_SLAB_KB': '128', 'ACB_LM_FILL': '60'}),
                                         ('lm_medium_2l', 3, {'ACB_LM_SLAB_KB': '24'})])
-def test_wide_step_matches_round1_kernels(monkeypatch, name, B, env):
-    """The default step (wide cluster-split-K GEMMs with the residual add + LayerNorm folded into producer and consumer,
-    8 kernels per layer) against the round-1 kernels (ACB_LM_STEP=v5: 16-feature tiles, split-K partials through global
-    memory, separate LayerNorm kernels, 11 per layer): same math, different summation grouping.  The env variants move
-    the tile plan (cluster sizes 1 / 2 / 4 / 8) so that every cluster width is exercised."""
+def test_wide_step_matches_default_kernels(monkeypatch, name, B, env):
+    """The opt-in v6 step (ACB_LM_STEP=v6: wide cluster-split-K GEMMs, DSMEM reduction, residual add + LayerNorm folded
+    into producer and consumer, 8 kernels per layer) against the default kernels (16-feature tiles, split-K partials
+    through global memory, separate LayerNorm kernels, 11 per layer): same math, different summation grouping.  The env
+    variants move the tile plan (cluster sizes 1 / 2 / 4 / 8) so that every cluster width is exercised."""
     cfg, sd, m = _model(name, 5)
     T = 6
     _, _, cross = H.lm_condition(cfg, sd, B, 5, 1)
     seq = torch.randint(0, cfg['card'], (B, 4, T + 4), generator=torch.Generator().manual_seed(1))
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    wide = m.teacher_forced_logits(seq, cross, 3.0).cpu()
-    n_wide = m.launches_per_step
-    monkeypatch.setenv('ACB_LM_STEP', 'v5')
     old = m.teacher_forced_logits(seq, cross, 3.0).cpu()
     n_old = m.launches_per_step
+    ref = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross).cpu()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setenv('ACB_LM_STEP', 'v6')
+    wide = m.teacher_forced_logits(seq, cross, 3.0).cpu()
+    n_wide = m.launches_per_step
+    out = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross).cpu()   # graph replay
     monkeypatch.delenv('ACB_LM_STEP')
     L = cfg['num_layers']
     assert n_wide == 8 * L + 3 and n_old == 11 * L + 4, (n_wide, n_old)
-    print(f'{name} B={B} {env}: max |wide - v5| = {(wide - old).abs().max():.2e} on |logits| <= {old.abs().max():.1f}')
+    print(f'{name} B={B} {env}: max |v6 - default| = {(wide - old).abs().max():.2e} on |logits| <= {old.abs().max():.1f}')
     torch.testing.assert_close(wide, old, rtol=0, atol=3e-2)
+    assert (out == ref).float().mean() > 0.9
 
 
 @pytest.mark.parametrize('name,B', [('lm_medium_2l', 8), ('lm_large_2l', 4), ('lm_large_2l', 32)])
