@@ -40,6 +40,15 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Debug timeline (ACB_LM_TIMING=1): thread 0 of every CTA writes %globaltimer (ns) into its 8-slot record.
+__device__ __forceinline__ void tl_stamp(unsigned long long* t, int slot) {
+    if (t && threadIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        t[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = now;
+    }
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -59,6 +68,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// TMA prefetch of a global range into L2 (no shared memory, no completion tracking).  16 B aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// This CTA's share of a grid-wide L2 prefetch of [base, base + bytes): called by one thread per CTA.
+__device__ __forceinline__ void grid_prefetch_l2(const unsigned char* base, size_t bytes) {
+    const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+    const size_t id = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const size_t share = ((bytes + ncta - 1) / ncta + 15) & ~(size_t)15;
+    const size_t lo = id * share;
+    if (lo >= bytes) return;
+    const size_t n = min(share, bytes - lo) & ~(size_t)15;
+    for (size_t o = 0; o < n; o += 32768) bulk_prefetch_l2(base + lo + o, (uint32_t)min((size_t)32768, n - o));
 }
 
 __device__ __forceinline__ float half_round(float v) { return __half2float(__float2half_rn(v)); }
@@ -120,11 +144,14 @@ constexpr int LN_MAX_PER_THREAD = 16;   // kept for the dim bound check (d <= 40
 constexpr int LN_THREADS = 256, LN_V4 = 4; // each thread owns up to LN_V4 float4 (d <= 4096)
 __global__ void __launch_bounds__(LN_THREADS) lm_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int nsplit,
                                                            size_t split_stride, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, __half* __restrict__ out, int d) {
+                                                           const float* __restrict__ beta, __half* __restrict__ out, int d,
+                                                           unsigned long long* timing) {
     __shared__ float red[2][32];
     const int r = blockIdx.x, d4 = d >> 2;
+    tl_stamp(timing, 0);
     pdl_trigger();
     pdl_wait();
+    tl_stamp(timing, 1);
     float4* xr = reinterpret_cast<float4*>(x + (size_t)r * d);
     float4 v[LN_V4];
     float s = 0.f;
@@ -172,6 +199,7 @@ __global__ void __launch_bounds__(LN_THREADS) lm_ln_kernel(float* __restrict__ x
             reinterpret_cast<uint2*>(out + (size_t)r * d)[i] = pk;
         }
     }
+    tl_stamp(timing, 3);
 }
 
 // ------------------------------------------------------------------------------------------------ skinny GEMM
@@ -185,6 +213,8 @@ struct GemmParams {
     __half* out_f16;                                   // GELU
     float* q32; __half* kc; __half* vc; int d, H, cache_len; const int* pos;  // QKV / CROSSKV
     int text_len, row0;                                                      // CROSSKV
+    const unsigned char* pf; size_t pf_bytes;   // weights of the NEXT GEMM of the step: prefetched into L2 by this grid
+    unsigned long long* timing;                 // debug timeline
 };
 
 // CTA = 4 warps, tile = 16 output features x kslice of K.  The CTA's 16 x kslice weight slab is fetched by ONE thread
@@ -203,6 +233,7 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
     uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + 16 * pitch);
     float* red = reinterpret_cast<float*>(gsm + 16 * pitch + 16);   // [4][16][RP]
 
+    tl_stamp(p.timing, 0);
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -211,8 +242,12 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
         for (int r = 0; r < 16; ++r)
             bulk_g2s(gsm + r * pitch, p.W + (size_t)(f0 + r) * p.K + k0, (uint32_t)ks * 2u, bar);
     }
+    // Keep HBM busy across the kernel boundary: while this GEMM streams its own weights (already on their way, or
+    // already in L2 thanks to the previous GEMM), the grid pulls the NEXT GEMM's weight matrix into L2.
+    if (tid == 32 && p.pf) grid_prefetch_l2(p.pf, p.pf_bytes);
     pdl_trigger();
     pdl_wait();   // activations written by the previous kernel are visible from here on
+    tl_stamp(p.timing, 1);
 
     float c[NT][4];
 #pragma unroll
@@ -249,6 +284,7 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
         }
     }
     if (!w_ready) mbar_wait(bar, 0);   // never leave with a bulk copy in flight
+    tl_stamp(p.timing, 2);
     // cross-warp (split-K inside the CTA) reduction in a fixed order
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -286,6 +322,7 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
             cache[(((size_t)r * p.H + h) * p.cache_len + tc) * 64 + dd] = __float2half_rn(v);
         }
     }
+    tl_stamp(p.timing, 3);
 }
 
 // ------------------------------------------------------------------------------------------------ wide skinny GEMM
@@ -615,6 +652,7 @@ struct AttnParams {
     const float* q; int q_nsplit; size_t q_split_stride;  // q[s][row][d] fp32 partial sums
     const __half* kc; const __half* vc; __half* out;
     int H, d, cache_len; const int* pos; int fixed_len; float scale;
+    unsigned long long* timing;   // debug timeline
 };
 
 // Self attention for one query token: CTA = (row, head), 8 warps, ONE pass over K and V with an online softmax.
@@ -636,8 +674,10 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     __shared__ float wm[ATT_WARPS], wl[ATT_WARPS], wacc[ATT_WARPS][64];
     const int h = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sl = lane & 7, pg = lane >> 3;
+    tl_stamp(p.timing, 0);
     pdl_trigger();
     pdl_wait();
+    tl_stamp(p.timing, 1);
     const int n = p.fixed_len > 0 ? p.fixed_len : p.pos[0] + 1;
 
     float q[8];
@@ -727,6 +767,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
         }
         p.out[(size_t)row * p.d + h * 64 + tid] = __float2half_rn(o / l);
     }
+    tl_stamp(p.timing, 3);
 }
 
 // Cross attention over the (short) text condition: one WARP per (row, head), lane = text position for the scores,
@@ -735,8 +776,10 @@ __global__ void __launch_bounds__(256) lm_cross_attn_kernel(AttnParams p, int ro
     __shared__ float qs[8][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = blockIdx.x * 8 + warp;          // (row, head) index
+    tl_stamp(p.timing, 0);
     pdl_trigger();
     pdl_wait();
+    tl_stamp(p.timing, 1);
     if (pair >= rows * p.H) return;                  // warp-uniform
     const int row = pair / p.H, h = pair % p.H, n = p.fixed_len;
 #pragma unroll
@@ -781,6 +824,7 @@ __global__ void __launch_bounds__(256) lm_cross_attn_kernel(AttnParams p, int ro
         mx = cm;
     }
     *reinterpret_cast<__half2*>(p.out + (size_t)row * p.d + h * 64 + lane * 2) = __floats2half2_rn(o0 / l, o1 / l);
+    tl_stamp(p.timing, 3);
 }
 
 // ------------------------------------------------------------------------------------------------ sampling
@@ -1193,7 +1237,7 @@ struct acb_lm {
     struct TimedGemm { const char* what; int ctas; };
     std::vector<TimedGemm> timed;
 };
-constexpr int ACB_TIMING_MAX_CTAS = 1024, ACB_TIMING_MAX_GEMMS = 8;
+constexpr int ACB_TIMING_MAX_CTAS = 1024, ACB_TIMING_MAX_GEMMS = 16;
 constexpr size_t ACB_PLAN_COUNTER_BYTES = 4096;   // first bytes of buffers.plan: one barrier counter per chain launch
 
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its
@@ -1269,6 +1313,11 @@ static GemmParams base_gemm(const void* W, const void* X, int N, int K, int rows
     p.X = (const __half*)X;
     p.N = N; p.K = K; p.rows = rows; p.kslice = kslice;
     return p;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
 }
 
 #define ACB_TRY(expr) do { int rc_ = (expr); if (rc_ != ACB_OK) return rc_; } while (0)
@@ -1426,19 +1475,61 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         ++nl;
         DBG("lm_embed_kernel", -1);
     }
+    // L2 prefetch chain: every GEMM pulls the weights of the next GEMM of the step (wrapping to layer 0) into L2
+    enum { G_QKV, G_O, G_CQ, G_CO, G_FF1, G_FF2, G_HEADS };
+    const bool prefetch = !env_int("ACB_LM_NO_PREFETCH", 0);
+    auto set_prefetch = [&](GemmParams& p, int l, int id) {
+        if (!prefetch) return;
+        int nl_ = l, nid = G_QKV;
+        switch (id) {
+            case G_QKV: nid = G_O; break;
+            case G_O: nid = lm->has_cross ? G_CQ : G_FF1; break;
+            case G_CQ: nid = G_CO; break;
+            case G_CO: nid = G_FF1; break;
+            case G_FF1: nid = G_FF2; break;
+            case G_FF2: if (l + 1 < L) { nl_ = l + 1; nid = G_QKV; } else nid = G_HEADS; break;
+            default: nl_ = 0; nid = G_QKV; break;
+        }
+        const size_t dd = (size_t)d * d;
+        const __half* w = nullptr;
+        size_t elems = 0;
+        switch (nid) {
+            case G_QKV: w = (const __half*)lm->w.w_qkv + (size_t)nl_ * 3 * dd; elems = 3 * dd; break;
+            case G_O: w = (const __half*)lm->w.w_o + (size_t)nl_ * dd; elems = dd; break;
+            case G_CQ: w = (const __half*)lm->w.w_cq + (size_t)nl_ * dd; elems = dd; break;
+            case G_CO: w = (const __half*)lm->w.w_co + (size_t)nl_ * dd; elems = dd; break;
+            case G_FF1: w = (const __half*)lm->w.w_ff1 + (size_t)nl_ * ffn * d; elems = (size_t)ffn * d; break;
+            case G_FF2: w = (const __half*)lm->w.w_ff2 + (size_t)nl_ * ffn * d; elems = (size_t)ffn * d; break;
+            default: w = (const __half*)lm->w.heads; elems = (size_t)c.n_q * c.card * d; break;
+        }
+        p.pf = reinterpret_cast<const unsigned char*>(w);
+        p.pf_bytes = elems * sizeof(__half);
+    };
+    // debug timeline (ACB_LM_TIMING=1): every kernel of layer 0 of a directly enqueued step gets a stamp buffer
+    if (lm->timing && !capturing) lm->timed.clear();
+    auto tl = [&](const char* what, int layer, int ctas) -> unsigned long long* {
+        if (!lm->timing || capturing || gemms_only || layer != 0 || (int)lm->timed.size() >= ACB_TIMING_MAX_GEMMS ||
+            ctas > ACB_TIMING_MAX_CTAS)
+            return nullptr;
+        unsigned long long* t = lm->timing + (size_t)lm->timed.size() * ACB_TIMING_MAX_CTAS * 8;
+        lm->timed.push_back({what, ctas});
+        return t;
+    };
     int pending = 0;  // split-K partial sums waiting to be folded into x by the next LN
     auto ln_launch = [&](const float* gamma, const float* beta, int layer) -> int {
         if (gemms_only) return ACB_OK;
         ACB_LAUNCH(lm_ln_kernel, dim3(rows), dim3(256), 0, s, pdl, B.x, (const float*)B.part, pending, part_stride, gamma, beta,
-                   (__half*)B.h16, d);
+                   (__half*)B.h16, d, tl("ln", layer, rows));
         ++nl;
         DBG("lm_ln_kernel", layer);
         return ACB_OK;
     };
-    auto partial_gemm = [&](const __half* W, const void* X, int N, int K, int layer) -> int {
+    auto partial_gemm = [&](const __half* W, const void* X, int N, int K, int layer, int id) -> int {
         const int ns = pick_split(N, K, lm->sms, true, &ks);
         GemmParams p = base_gemm(W, X, N, K, rows, ks);
         p.out_f32 = B.part; p.ld_out = N; p.split_stride = part_stride;
+        set_prefetch(p, layer, id);
+        p.timing = tl(id == G_O ? "gemm_O" : (id == G_CQ ? "gemm_CQ" : (id == G_CO ? "gemm_CO" : "gemm_FFN2")), layer, (N / 16) * ns);
         ACB_TRY(launch_gemm<EPI_PARTIAL>(nt, p, ns, s, pdl));
         ++nl;
         DBG("gemm_EPI_PARTIAL", layer);
@@ -1454,32 +1545,36 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             GemmParams p = base_gemm((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, B.h16, 3 * d, d, rows, ks);
             p.q32 = B.q32; p.kc = (__half*)B.k_cache + l * kv_layer; p.vc = (__half*)B.v_cache + l * kv_layer;
             p.d = d; p.H = H; p.cache_len = c.max_seq; p.pos = B.pos;
+            set_prefetch(p, l, G_QKV);
+            p.timing = tl("gemm_QKV", l, 3 * d / 16);
             ACB_TRY(launch_gemm<EPI_QKV>(nt, p, 1, s, pdl)); ++nl;
             DBG("gemm_EPI_QKV", l);
         }
         if (!gemms_only) {
             AttnParams a{B.q32, 1, 0, (__half*)B.k_cache + l * kv_layer, (__half*)B.v_cache + l * kv_layer, (__half*)B.a16,
                          H, d, c.max_seq, B.pos, 0, scale};
+            a.timing = tl("attn", l, H * rows);
             ACB_LAUNCH(lm_attn_kernel, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
             ++nl;
             DBG("lm_attn_kernel", l);
         }
-        ACB_TRY(partial_gemm((const __half*)lm->w.w_o + (size_t)l * d * d, B.a16, d, d, l));
+        ACB_TRY(partial_gemm((const __half*)lm->w.w_o + (size_t)l * d * d, B.a16, d, d, l, G_O));
         // --- cross attention
         if (lm->has_cross) {
             ACB_TRY(ln_launch(ln + 2 * d, ln + 3 * d, l));
-            ACB_TRY(partial_gemm((const __half*)lm->w.w_cq + (size_t)l * d * d, B.h16, d, d, l));
+            ACB_TRY(partial_gemm((const __half*)lm->w.w_cq + (size_t)l * d * d, B.h16, d, d, l, G_CQ));
             const int nsq = pending;
             pending = 0;   // these partials are the cross-attention queries, not a residual update
             if (!gemms_only) {
                 AttnParams a{B.part, nsq, part_stride, (__half*)B.ck_cache + l * ckv_layer,
                              (__half*)B.cv_cache + l * ckv_layer, (__half*)B.a16, H, d, c.max_text, B.pos, lm->text_len,
                              scale};
+                a.timing = tl("cross_attn", l, acb_ceil_div(rows * H, 8));
                 ACB_LAUNCH(lm_cross_attn_kernel, dim3(acb_ceil_div(rows * H, 8)), dim3(256), 0, s, pdl, a, rows);
                 ++nl;
                 DBG("lm_cross_attn_kernel", l);
             }
-            ACB_TRY(partial_gemm((const __half*)lm->w.w_co + (size_t)l * d * d, B.a16, d, d, l));
+            ACB_TRY(partial_gemm((const __half*)lm->w.w_co + (size_t)l * d * d, B.a16, d, d, l, G_CO));
         }
         // --- feed forward
         ACB_TRY(ln_launch(ln + 4 * d, ln + 5 * d, l));
@@ -1487,10 +1582,12 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             pick_split(ffn, d, lm->sms, false, &ks);
             GemmParams p = base_gemm((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, B.h16, ffn, d, rows, ks);
             p.out_f16 = (__half*)B.f16; p.ld_out = ffn;
+            set_prefetch(p, l, G_FF1);
+            p.timing = tl("gemm_FFN1", l, ffn / 16);
             ACB_TRY(launch_gemm<EPI_GELU>(nt, p, 1, s, pdl)); ++nl;
             DBG("gemm_EPI_GELU", l);
         }
-        ACB_TRY(partial_gemm((const __half*)lm->w.w_ff2 + (size_t)l * d * ffn, B.f16, d, ffn, l));
+        ACB_TRY(partial_gemm((const __half*)lm->w.w_ff2 + (size_t)l * d * ffn, B.f16, d, ffn, l, G_FF2));
     }
     ACB_TRY(ln_launch(lm->w.out_norm, lm->w.out_norm + d, -1));
     {
@@ -1498,6 +1595,7 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         pick_split(N, d, lm->sms, false, &ks);
         GemmParams p = base_gemm(lm->w.heads, B.h16, N, d, rows, ks);
         p.out_f32 = B.logits; p.ld_out = N;
+        set_prefetch(p, L, G_HEADS);
         ACB_TRY(launch_gemm<EPI_F32>(nt, p, 1, s, pdl)); ++nl;
         DBG("gemm_EPI_F32", -1);
     }
@@ -1518,10 +1616,6 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
 
 // ---- v6 step: wide GEMMs with cluster split-K and LayerNorm folded into producer / consumer (8 kernels per layer)
 struct WTile { int fg, ns, kslice; };
-static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return (e && e[0]) ? atoi(e) : dflt;
-}
 // Tile plan of one GEMM: 32 features per CTA (16 when N is not a multiple of 32), and K cut into `ns` cluster slices
 // until the slab fits ACB_LM_SLAB_KB (default 56 KB: three CTAs per SM stay co-resident, which is what lets the next
 // kernel's weight prefetch overlap under PDL) and the grid covers ACB_LM_FILL % of the SMs (default 90).
@@ -1961,9 +2055,38 @@ static int report_timing(acb_lm* lm, cudaStream_t s) {
     return ACB_OK;
 }
 
+// Debug timeline of the default step's layer-0 kernels (%globaltimer, ns, relative to the first CTA of the first kernel):
+// CTA starts (first..last), when griddepcontrol.wait returned (median), the kernel's mid stamp (GEMM: weights + k-loop
+// done; median), CTA ends (median..last).
+static int report_timeline(acb_lm* lm, cudaStream_t s) {
+    ACB_CHECK_CUDA(cudaStreamSynchronize(s));
+    std::vector<unsigned long long> h((size_t)ACB_TIMING_MAX_CTAS * 8);
+    unsigned long long t0 = 0;
+    for (size_t gi = 0; gi < lm->timed.size(); ++gi) {
+        const int n = lm->timed[gi].ctas;
+        ACB_CHECK_CUDA(cudaMemcpy(h.data(), lm->timing + gi * ACB_TIMING_MAX_CTAS * 8, (size_t)n * 64, cudaMemcpyDeviceToHost));
+        std::vector<long long> col[4];
+        for (int i = 0; i < n; ++i)
+            for (int sl = 0; sl < 4; ++sl)
+                if (h[i * 8 + sl]) col[sl].push_back((long long)h[i * 8 + sl]);
+        for (auto& v : col) std::sort(v.begin(), v.end());
+        if (col[0].empty()) continue;
+        if (!t0) t0 = (unsigned long long)col[0].front();
+        auto rel = [&](long long v) { return v - (long long)t0; };
+        fprintf(stderr, "[acb timeline] %-10s %4d CTAs  start %6lld..%6lld", lm->timed[gi].what, n, rel(col[0].front()), rel(col[0].back()));
+        if (!col[1].empty()) fprintf(stderr, "  wait-returned %6lld (med) %6lld (max)", rel(col[1][col[1].size() / 2]), rel(col[1].back()));
+        if (!col[2].empty()) fprintf(stderr, "  k-loop done %6lld (med) %6lld (max)", rel(col[2][col[2].size() / 2]), rel(col[2].back()));
+        if (!col[3].empty()) fprintf(stderr, "  end %6lld (med) %6lld (max)", rel(col[3][col[3].size() / 2]), rel(col[3].back()));
+        fprintf(stderr, "  [ns]\n");
+    }
+    ACB_CHECK_CUDA(cudaMemset(lm->timing, 0, (size_t)ACB_TIMING_MAX_GEMMS * ACB_TIMING_MAX_CTAS * 64));
+    return ACB_OK;
+}
+
 extern "C" int acb_lm_step_logits(acb_lm_t* lm, float* logits_out, void* stream) {
     ACB_REQUIRE(lm && lm->rows > 0, "acb_lm_step_logits: call acb_lm_begin first");
     ACB_TRY(enqueue_step(lm, (cudaStream_t)stream, logits_out, nullptr));
+    if (lm->timing && !lm->wide && !lm->chain) ACB_TRY(report_timeline(lm, (cudaStream_t)stream));
     if (lm->timing && lm->wide && !lm->chain) ACB_TRY(report_timing(lm, (cudaStream_t)stream));
     return ACB_OK;
 }

@@ -1,0 +1,6 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+echo "== pytest lm"; timeout 900 python -m pytest tests/test_gpu_lm.py -x -q -m gpu > gpurun_out/pf_pytest_lm.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pf_pytest_lm.log
+echo "== perf prefetch"; timeout 300 python profiles/perf_lm_step.py > gpurun_out/pf_perf.log 2>&1; cat gpurun_out/pf_perf.log
+echo "== perf no prefetch"; ACB_LM_NO_PREFETCH=1 timeout 300 python profiles/perf_lm_step.py > gpurun_out/pf_perf_off.log 2>&1; cat gpurun_out/pf_perf_off.log
