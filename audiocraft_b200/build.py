@@ -17,9 +17,9 @@ SOURCES = ['api.cu', 'encodec.cu', 'lm.cu']
 HEADERS = ['common.cuh', os.path.join('..', '..', 'include', 'audiocraft_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC',
-         '--use_fast_math=false'] if False else \
-        ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC',
          '-Xptxas', '-v']
+if os.environ.get('ACB_BUILD_TIMELINE') == '1':   # instrumented build: in-kernel %globaltimer stamps (see csrc/lm.cu tl_stamp)
+    FLAGS.append('-DACB_TIMELINE')
 
 
 def _digest() -> str:

@@ -40,7 +40,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// Debug timeline (ACB_LM_TIMING=1): thread 0 of every CTA writes %globaltimer (ns) into its 8-slot record.
+// Debug timeline: thread 0 of every CTA writes %globaltimer (ns) into its 8-slot record.  Compiled in only with
+// -DACB_TIMELINE (ACB_BUILD_TIMELINE=1 python -m audiocraft_b200.build) and armed with ACB_LM_TIMING=1: at this time
+// scale even the dormant stamps cost (532 kernels x ~0.3 us measured), because every instruction line of a 3 us kernel is
+// fetched cold.
+#ifdef ACB_TIMELINE
 __device__ __forceinline__ void tl_stamp(unsigned long long* t, int slot) {
     if (t && threadIdx.x == 0) {
         unsigned long long now;
@@ -48,6 +52,9 @@ __device__ __forceinline__ void tl_stamp(unsigned long long* t, int slot) {
         t[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = now;
     }
 }
+#else
+__device__ __forceinline__ void tl_stamp(unsigned long long*, int) {}
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -68,21 +75,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// TMA prefetch of a global range into L2 (no shared memory, no completion tracking).  16 B aligned, size % 16 == 0.
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-// This CTA's share of a grid-wide L2 prefetch of [base, base + bytes): called by one thread per CTA.
-__device__ __forceinline__ void grid_prefetch_l2(const unsigned char* base, size_t bytes) {
-    const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
-    const size_t id = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    const size_t share = ((bytes + ncta - 1) / ncta + 15) & ~(size_t)15;
-    const size_t lo = id * share;
-    if (lo >= bytes) return;
-    const size_t n = min(share, bytes - lo) & ~(size_t)15;
-    for (size_t o = 0; o < n; o += 32768) bulk_prefetch_l2(base + lo + o, (uint32_t)min((size_t)32768, n - o));
 }
 
 __device__ __forceinline__ float half_round(float v) { return __half2float(__float2half_rn(v)); }
@@ -140,64 +132,57 @@ __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict_
 
 // ------------------------------------------------------------------------------------------------ residual + LN
 // x[r] += sum_s part[s][r] (fixed order), then h16[r] = LayerNorm(x[r]) * gamma + beta  (eps 1e-5, fp32 statistics).
-constexpr int LN_MAX_PER_THREAD = 16;   // kept for the dim bound check (d <= 4096)
-constexpr int LN_THREADS = 256, LN_V4 = 4; // each thread owns up to LN_V4 float4 (d <= 4096)
+// One CTA per row, ONE float4 per thread (d <= 2048): no per-thread loops, so the kernel is ~300 instructions -- at this
+// time scale cold instruction fetch is a first-order cost (the 4-float4-per-thread version was 1 048 instructions and
+// spent 1-2 us before its first load was consumed).  gamma / beta do not depend on the previous kernel and are
+// requested before griddepcontrol.wait.
+constexpr int LN_MAX_PER_THREAD = 16;   // kept for the dim bound check in acb_lm_create
+constexpr int LN_THREADS = 512;
 __global__ void __launch_bounds__(LN_THREADS) lm_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int nsplit,
                                                            size_t split_stride, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, __half* __restrict__ out, int d,
                                                            unsigned long long* timing) {
     __shared__ float red[2][32];
-    const int r = blockIdx.x, d4 = d >> 2;
+    const int r = blockIdx.x, i = threadIdx.x;
+    const bool live = i < (d >> 2);
     tl_stamp(timing, 0);
+    float4 gm = make_float4(0.f, 0.f, 0.f, 0.f), bt = gm;
+    if (live) { gm = reinterpret_cast<const float4*>(gamma)[i]; bt = reinterpret_cast<const float4*>(beta)[i]; }
     pdl_trigger();
     pdl_wait();
     tl_stamp(timing, 1);
     float4* xr = reinterpret_cast<float4*>(x + (size_t)r * d);
-    float4 v[LN_V4];
-    float s = 0.f;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        a = xr[i];
+        float4 pt[ACB_LM_MAX_SPLIT];
 #pragma unroll
-    for (int j = 0; j < LN_V4; ++j) {
-        const int i = threadIdx.x + j * LN_THREADS;
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < d4) {
-            float4 a = xr[i];
-            float4 pt[ACB_LM_MAX_SPLIT];
+        for (int sp = 0; sp < ACB_LM_MAX_SPLIT; ++sp)   // independent loads, all in flight together
+            pt[sp] = sp < nsplit ? reinterpret_cast<const float4*>(part + sp * split_stride + (size_t)r * d)[i]
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int sp = 0; sp < ACB_LM_MAX_SPLIT; ++sp)   // independent loads, all in flight together
-                pt[sp] = sp < nsplit ? reinterpret_cast<const float4*>(part + sp * split_stride + (size_t)r * d)[i]
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int sp = 0; sp < ACB_LM_MAX_SPLIT; ++sp) {  // fixed summation order
-                a.x += pt[sp].x; a.y += pt[sp].y; a.z += pt[sp].z; a.w += pt[sp].w;
-            }
-            if (nsplit) xr[i] = a;
-            v[j] = a;
-            s += (a.x + a.y) + (a.z + a.w);
+        for (int sp = 0; sp < ACB_LM_MAX_SPLIT; ++sp) {  // fixed summation order
+            a.x += pt[sp].x; a.y += pt[sp].y; a.z += pt[sp].z; a.w += pt[sp].w;
         }
+        if (nsplit) xr[i] = a;
     }
-    const float mean = block_sum(s, red[0]) / d;
+    tl_stamp(timing, 4);
+    const float mean = block_sum((a.x + a.y) + (a.z + a.w), red[0]) / d;
+    tl_stamp(timing, 5);
     float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < LN_V4; ++j) {
-        const int i = threadIdx.x + j * LN_THREADS;
-        if (i < d4) {
-            float cx = v[j].x - mean, cy = v[j].y - mean, cz = v[j].z - mean, cw = v[j].w - mean;
-            q = fmaf(cx, cx, q); q = fmaf(cy, cy, q); q = fmaf(cz, cz, q); q = fmaf(cw, cw, q);
-        }
+    if (live) {
+        const float cx = a.x - mean, cy = a.y - mean, cz = a.z - mean, cw = a.w - mean;
+        q = fmaf(cx, cx, q); q = fmaf(cy, cy, q); q = fmaf(cz, cz, q); q = fmaf(cw, cw, q);
     }
     const float rstd = 1.f / sqrtf(block_sum(q, red[1]) / d + 1e-5f);
-#pragma unroll
-    for (int j = 0; j < LN_V4; ++j) {
-        const int i = threadIdx.x + j * LN_THREADS;
-        if (i < d4) {
-            const float4 gm = reinterpret_cast<const float4*>(gamma)[i], bt = reinterpret_cast<const float4*>(beta)[i];
-            __half2 lo = __floats2half2_rn((v[j].x - mean) * rstd * gm.x + bt.x, (v[j].y - mean) * rstd * gm.y + bt.y);
-            __half2 hi = __floats2half2_rn((v[j].z - mean) * rstd * gm.z + bt.z, (v[j].w - mean) * rstd * gm.w + bt.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            reinterpret_cast<uint2*>(out + (size_t)r * d)[i] = pk;
-        }
+    tl_stamp(timing, 6);
+    if (live) {
+        __half2 lo = __floats2half2_rn((a.x - mean) * rstd * gm.x + bt.x, (a.y - mean) * rstd * gm.y + bt.y);
+        __half2 hi = __floats2half2_rn((a.z - mean) * rstd * gm.z + bt.z, (a.w - mean) * rstd * gm.w + bt.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(out + (size_t)r * d)[i] = pk;
     }
     tl_stamp(timing, 3);
 }
@@ -213,7 +198,6 @@ struct GemmParams {
     __half* out_f16;                                   // GELU
     float* q32; __half* kc; __half* vc; int d, H, cache_len; const int* pos;  // QKV / CROSSKV
     int text_len, row0;                                                      // CROSSKV
-    const unsigned char* pf; size_t pf_bytes;   // weights of the NEXT GEMM of the step: prefetched into L2 by this grid
     unsigned long long* timing;                 // debug timeline
 };
 
@@ -242,12 +226,11 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
         for (int r = 0; r < 16; ++r)
             bulk_g2s(gsm + r * pitch, p.W + (size_t)(f0 + r) * p.K + k0, (uint32_t)ks * 2u, bar);
     }
-    // Keep HBM busy across the kernel boundary: while this GEMM streams its own weights (already on their way, or
-    // already in L2 thanks to the previous GEMM), the grid pulls the NEXT GEMM's weight matrix into L2.
-    if (tid == 32 && p.pf) grid_prefetch_l2(p.pf, p.pf_bytes);
     pdl_trigger();
     pdl_wait();   // activations written by the previous kernel are visible from here on
     tl_stamp(p.timing, 1);
+    int cache_pos = 0;
+    if (EPI == EPI_QKV) cache_pos = p.pos[0];   // requested now, consumed in the epilogue: off the critical path
 
     float c[NT][4];
 #pragma unroll
@@ -269,7 +252,7 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
             for (int j = 0; j < NT; ++j)
                 xv[u][j] = (kb + u < kb1) ? *reinterpret_cast<const uint4*>(xr + (size_t)(8 * j) * p.K + (size_t)(kb + u) * 32)
                                           : make_uint4(0, 0, 0, 0);
-        if (!w_ready) { mbar_wait(bar, 0); w_ready = true; }
+        if (!w_ready) { mbar_wait(bar, 0); w_ready = true; tl_stamp(p.timing, 4); }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (kb + u < kb1) {
@@ -294,6 +277,7 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
         red[(warp * 16 + g + 8) * RP + 8 * j + 2 * c4 + 1] = c[j][3];
     }
     __syncthreads();
+    tl_stamp(p.timing, 5);
     for (int idx = tid; idx < 16 * 8 * NT; idx += 128) {
         const int row = idx >> 4, feat = idx & 15;
         if (row >= p.rows) continue;
@@ -313,7 +297,7 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
             } else {
                 const int which = (n - p.d) / p.d, nn = n % p.d, h = nn >> 6, dd = nn & 63;
                 __half* cache = which ? p.vc : p.kc;
-                cache[(((size_t)row * p.H + h) * p.cache_len + p.pos[0]) * 64 + dd] = __float2half_rn(v);
+                cache[(((size_t)row * p.H + h) * p.cache_len + cache_pos) * 64 + dd] = __float2half_rn(v);
             }
         } else {  // EPI_CROSSKV: GEMM rows are (row, text position) pairs
             const int R = p.row0 + row, r = R / p.text_len, tc = R % p.text_len;
@@ -363,6 +347,7 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t local_smem_addr, uint32_
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(cta_rank));
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
+#ifdef ACB_TIMELINE
 __device__ __forceinline__ void wg_stamp(const WGemmParams& p, int slot) {
     if (p.timing && threadIdx.x == 0) {
         unsigned long long t;
@@ -371,6 +356,9 @@ __device__ __forceinline__ void wg_stamp(const WGemmParams& p, int slot) {
         p.timing[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
     }
 }
+#else
+__device__ __forceinline__ void wg_stamp(const WGemmParams&, int) {}
+#endif
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -681,12 +669,15 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     const int n = p.fixed_len > 0 ? p.fixed_len : p.pos[0] + 1;
 
     float q[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        float a = 0.f;
-        for (int s = 0; s < p.q_nsplit; ++s) a += p.q[s * p.q_split_stride + (size_t)row * p.d + h * 64 + sl * 8 + e];
-        q[e] = half_round(a) * p.scale;
+    {   // (split-K query partials exist only on the cross-attention path; a rolled/unrolled split loop here cost
+        //  ~1 500 instructions of cold code per launch)
+        const float4* qp = reinterpret_cast<const float4*>(p.q + (size_t)row * p.d + h * 64 + sl * 8);
+        const float4 qa = qp[0], qb = qp[1];
+        q[0] = half_round(qa.x) * p.scale; q[1] = half_round(qa.y) * p.scale; q[2] = half_round(qa.z) * p.scale;
+        q[3] = half_round(qa.w) * p.scale; q[4] = half_round(qb.x) * p.scale; q[5] = half_round(qb.y) * p.scale;
+        q[6] = half_round(qb.z) * p.scale; q[7] = half_round(qb.w) * p.scale;
     }
+    tl_stamp(p.timing, 4);   // n and q consumed
     const size_t base = ((size_t)row * p.H + h) * p.cache_len * 64 + sl * 8;
     const __half* kb = p.kc + base;
     const __half* vb = p.vc + base;
@@ -739,6 +730,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
             }
         }
     }
+    tl_stamp(p.timing, 2);   // position loop
     // merge the 4 position groups of the warp, then the warps
 #pragma unroll
     for (int o = 8; o <= 16; o <<= 1) {
@@ -748,12 +740,14 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
         for (int e = 0; e < 8; ++e) a2[e] = __shfl_xor_sync(0xffffffffu, st.acc[e], o);
         osm_merge(st, m2, l2, a2);
     }
+    tl_stamp(p.timing, 5);   // lane merges
     if (pg == 0) {
         if (sl == 0) { wm[warp] = st.m; wl[warp] = st.l; }
 #pragma unroll
         for (int e = 0; e < 8; ++e) wacc[warp][sl * 8 + e] = st.acc[e];
     }
     __syncthreads();
+    tl_stamp(p.timing, 6);
     if (tid < 64) {
         float mx = wm[0];
 #pragma unroll
@@ -782,13 +776,20 @@ __global__ void __launch_bounds__(256) lm_cross_attn_kernel(AttnParams p, int ro
     tl_stamp(p.timing, 1);
     if (pair >= rows * p.H) return;                  // warp-uniform
     const int row = pair / p.H, h = pair % p.H, n = p.fixed_len;
+    {
+        const float* qp = p.q + (size_t)row * p.d + h * 64 + lane * 2;
+        float2 part[ACB_LM_MAX_SPLIT];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        float a = 0.f;
-        for (int s = 0; s < p.q_nsplit; ++s) a += p.q[s * p.q_split_stride + (size_t)row * p.d + h * 64 + lane * 2 + e];
-        qs[warp][lane * 2 + e] = half_round(a) * p.scale;
+        for (int s = 0; s < ACB_LM_MAX_SPLIT; ++s)   // independent loads, fixed summation order
+            part[s] = s < p.q_nsplit ? *reinterpret_cast<const float2*>(qp + s * p.q_split_stride) : make_float2(0.f, 0.f);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int s = 0; s < ACB_LM_MAX_SPLIT; ++s) { a0 += part[s].x; a1 += part[s].y; }
+        qs[warp][lane * 2] = half_round(a0) * p.scale;
+        qs[warp][lane * 2 + 1] = half_round(a1) * p.scale;
     }
     __syncwarp();
+    tl_stamp(p.timing, 4);
     const size_t base = ((size_t)row * p.H + h) * p.cache_len * 64;
     float mx = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
     for (int t0 = 0; t0 < n; t0 += 32) {             // chunks of 32 text positions (online softmax across chunks)
@@ -809,11 +810,13 @@ __global__ void __launch_bounds__(256) lm_cross_attn_kernel(AttnParams p, int ro
                 }
             }
         }
+        tl_stamp(p.timing, 5);
         const float cm = fmaxf(mx, warp_max(s));
         const float corr = mx == -INFINITY ? 0.f : __expf(mx - cm);
         const float pw = t < n ? __expf(s - cm) : 0.f;
         l = l * corr + warp_sum(pw);
         o0 *= corr; o1 *= corr;
+        tl_stamp(p.timing, 6);
         const int cnt = min(32, n - t0);
         for (int j = 0; j < cnt; ++j) {
             const float wj = __shfl_sync(0xffffffffu, pw, j);
@@ -823,6 +826,7 @@ __global__ void __launch_bounds__(256) lm_cross_attn_kernel(AttnParams p, int ro
         }
         mx = cm;
     }
+    tl_stamp(p.timing, 2);
     *reinterpret_cast<__half2*>(p.out + (size_t)row * p.d + h * 64 + lane * 2) = __floats2half2_rn(o0 / l, o1 / l);
     tl_stamp(p.timing, 3);
 }
@@ -1475,36 +1479,10 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         ++nl;
         DBG("lm_embed_kernel", -1);
     }
-    // L2 prefetch chain: every GEMM pulls the weights of the next GEMM of the step (wrapping to layer 0) into L2
+    // (An L2 prefetch chain -- every GEMM pulling the NEXT GEMM's weights into L2 with cp.async.bulk.prefetch.L2 -- was
+    //  built and measured: 2.240 vs 2.258 ms per step, i.e. nothing: under PDL the weight slab is already in flight before
+    //  the dependency resolves, weights are not on the critical path.  profiles/r1_perf_step_v5_l2prefetch_no_gain.log)
     enum { G_QKV, G_O, G_CQ, G_CO, G_FF1, G_FF2, G_HEADS };
-    const bool prefetch = !env_int("ACB_LM_NO_PREFETCH", 0);
-    auto set_prefetch = [&](GemmParams& p, int l, int id) {
-        if (!prefetch) return;
-        int nl_ = l, nid = G_QKV;
-        switch (id) {
-            case G_QKV: nid = G_O; break;
-            case G_O: nid = lm->has_cross ? G_CQ : G_FF1; break;
-            case G_CQ: nid = G_CO; break;
-            case G_CO: nid = G_FF1; break;
-            case G_FF1: nid = G_FF2; break;
-            case G_FF2: if (l + 1 < L) { nl_ = l + 1; nid = G_QKV; } else nid = G_HEADS; break;
-            default: nl_ = 0; nid = G_QKV; break;
-        }
-        const size_t dd = (size_t)d * d;
-        const __half* w = nullptr;
-        size_t elems = 0;
-        switch (nid) {
-            case G_QKV: w = (const __half*)lm->w.w_qkv + (size_t)nl_ * 3 * dd; elems = 3 * dd; break;
-            case G_O: w = (const __half*)lm->w.w_o + (size_t)nl_ * dd; elems = dd; break;
-            case G_CQ: w = (const __half*)lm->w.w_cq + (size_t)nl_ * dd; elems = dd; break;
-            case G_CO: w = (const __half*)lm->w.w_co + (size_t)nl_ * dd; elems = dd; break;
-            case G_FF1: w = (const __half*)lm->w.w_ff1 + (size_t)nl_ * ffn * d; elems = (size_t)ffn * d; break;
-            case G_FF2: w = (const __half*)lm->w.w_ff2 + (size_t)nl_ * ffn * d; elems = (size_t)ffn * d; break;
-            default: w = (const __half*)lm->w.heads; elems = (size_t)c.n_q * c.card * d; break;
-        }
-        p.pf = reinterpret_cast<const unsigned char*>(w);
-        p.pf_bytes = elems * sizeof(__half);
-    };
     // debug timeline (ACB_LM_TIMING=1): every kernel of layer 0 of a directly enqueued step gets a stamp buffer
     if (lm->timing && !capturing) lm->timed.clear();
     auto tl = [&](const char* what, int layer, int ctas) -> unsigned long long* {
@@ -1518,7 +1496,7 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
     int pending = 0;  // split-K partial sums waiting to be folded into x by the next LN
     auto ln_launch = [&](const float* gamma, const float* beta, int layer) -> int {
         if (gemms_only) return ACB_OK;
-        ACB_LAUNCH(lm_ln_kernel, dim3(rows), dim3(256), 0, s, pdl, B.x, (const float*)B.part, pending, part_stride, gamma, beta,
+        ACB_LAUNCH(lm_ln_kernel, dim3(rows), dim3(LN_THREADS), 0, s, pdl, B.x, (const float*)B.part, pending, part_stride, gamma, beta,
                    (__half*)B.h16, d, tl("ln", layer, rows));
         ++nl;
         DBG("lm_ln_kernel", layer);
@@ -1528,7 +1506,6 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         const int ns = pick_split(N, K, lm->sms, true, &ks);
         GemmParams p = base_gemm(W, X, N, K, rows, ks);
         p.out_f32 = B.part; p.ld_out = N; p.split_stride = part_stride;
-        set_prefetch(p, layer, id);
         p.timing = tl(id == G_O ? "gemm_O" : (id == G_CQ ? "gemm_CQ" : (id == G_CO ? "gemm_CO" : "gemm_FFN2")), layer, (N / 16) * ns);
         ACB_TRY(launch_gemm<EPI_PARTIAL>(nt, p, ns, s, pdl));
         ++nl;
@@ -1545,7 +1522,6 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             GemmParams p = base_gemm((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, B.h16, 3 * d, d, rows, ks);
             p.q32 = B.q32; p.kc = (__half*)B.k_cache + l * kv_layer; p.vc = (__half*)B.v_cache + l * kv_layer;
             p.d = d; p.H = H; p.cache_len = c.max_seq; p.pos = B.pos;
-            set_prefetch(p, l, G_QKV);
             p.timing = tl("gemm_QKV", l, 3 * d / 16);
             ACB_TRY(launch_gemm<EPI_QKV>(nt, p, 1, s, pdl)); ++nl;
             DBG("gemm_EPI_QKV", l);
@@ -1582,7 +1558,6 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             pick_split(ffn, d, lm->sms, false, &ks);
             GemmParams p = base_gemm((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, B.h16, ffn, d, rows, ks);
             p.out_f16 = (__half*)B.f16; p.ld_out = ffn;
-            set_prefetch(p, l, G_FF1);
             p.timing = tl("gemm_FFN1", l, ffn / 16);
             ACB_TRY(launch_gemm<EPI_GELU>(nt, p, 1, s, pdl)); ++nl;
             DBG("gemm_EPI_GELU", l);
@@ -1595,7 +1570,6 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         pick_split(N, d, lm->sms, false, &ks);
         GemmParams p = base_gemm(lm->w.heads, B.h16, N, d, rows, ks);
         p.out_f32 = B.logits; p.ld_out = N;
-        set_prefetch(p, L, G_HEADS);
         ACB_TRY(launch_gemm<EPI_F32>(nt, p, 1, s, pdl)); ++nl;
         DBG("gemm_EPI_F32", -1);
     }
@@ -1876,7 +1850,7 @@ extern "C" int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, 
     ACB_REQUIRE(cfg && w && buf && out, "acb_lm_create: null argument");
     ACB_REQUIRE(cfg->dim % 64 == 0 && cfg->dim == cfg->num_heads * 64, "acb_lm_create: head_dim must be 64 (dim=%d heads=%d)",
                 cfg->dim, cfg->num_heads);
-    ACB_REQUIRE(cfg->dim <= 256 * LN_MAX_PER_THREAD, "acb_lm_create: dim %d too large", cfg->dim);
+    ACB_REQUIRE(cfg->dim <= 4 * LN_THREADS, "acb_lm_create: dim %d too large for the LayerNorm kernel", cfg->dim);
     ACB_REQUIRE(cfg->ffn_dim % 32 == 0 && cfg->card % 16 == 0 && cfg->n_q >= 1 && cfg->n_q <= 16, "acb_lm_create: bad ffn/card/n_q");
     ACB_REQUIRE(cfg->card <= 4096, "acb_lm_create: card %d > 4096 not built", cfg->card);
     ACB_REQUIRE(cfg->max_rows >= 1 && cfg->max_rows <= 64, "acb_lm_create: max_rows %d not in [1,64]", cfg->max_rows);
@@ -2065,19 +2039,23 @@ static int report_timeline(acb_lm* lm, cudaStream_t s) {
     for (size_t gi = 0; gi < lm->timed.size(); ++gi) {
         const int n = lm->timed[gi].ctas;
         ACB_CHECK_CUDA(cudaMemcpy(h.data(), lm->timing + gi * ACB_TIMING_MAX_CTAS * 8, (size_t)n * 64, cudaMemcpyDeviceToHost));
-        std::vector<long long> col[4];
+        std::vector<long long> col[8];
         for (int i = 0; i < n; ++i)
-            for (int sl = 0; sl < 4; ++sl)
+            for (int sl = 0; sl < 8; ++sl)
                 if (h[i * 8 + sl]) col[sl].push_back((long long)h[i * 8 + sl]);
         for (auto& v : col) std::sort(v.begin(), v.end());
-        if (col[0].empty()) continue;
+        if (col[0].empty() || col[1].empty() || col[3].empty()) continue;
         if (!t0) t0 = (unsigned long long)col[0].front();
-        auto rel = [&](long long v) { return v - (long long)t0; };
-        fprintf(stderr, "[acb timeline] %-10s %4d CTAs  start %6lld..%6lld", lm->timed[gi].what, n, rel(col[0].front()), rel(col[0].back()));
-        if (!col[1].empty()) fprintf(stderr, "  wait-returned %6lld (med) %6lld (max)", rel(col[1][col[1].size() / 2]), rel(col[1].back()));
-        if (!col[2].empty()) fprintf(stderr, "  k-loop done %6lld (med) %6lld (max)", rel(col[2][col[2].size() / 2]), rel(col[2].back()));
-        if (!col[3].empty()) fprintf(stderr, "  end %6lld (med) %6lld (max)", rel(col[3][col[3].size() / 2]), rel(col[3].back()));
-        fprintf(stderr, "  [ns]\n");
+        const long long w = col[1][col[1].size() / 2];   // median wait-return
+        fprintf(stderr, "[acb timeline] %-10s %4d CTAs  start %6lld..%6lld  wait-returned %6lld  end %6lld (med) %6lld (max) | after wait [ns, median]:",
+                lm->timed[gi].what, n, col[0].front() - (long long)t0, col[0].back() - (long long)t0, w - (long long)t0,
+                col[3][col[3].size() / 2] - (long long)t0, col[3].back() - (long long)t0);
+        static const int order[6] = {4, 5, 6, 7, 2, 3};   // stamps in program order (2 = main loop done, 3 = end)
+        for (int oi = 0; oi < 6; ++oi) {
+            const std::vector<long long>& v = col[order[oi]];
+            if (!v.empty()) fprintf(stderr, "  s%d %lld", order[oi], v[v.size() / 2] - w);
+        }
+        fprintf(stderr, "\n");
     }
     ACB_CHECK_CUDA(cudaMemset(lm->timing, 0, (size_t)ACB_TIMING_MAX_GEMMS * ACB_TIMING_MAX_CTAS * 64));
     return ACB_OK;

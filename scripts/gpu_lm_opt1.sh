@@ -1,0 +1,6 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+echo "== pytest lm"; timeout 900 python -m pytest tests/test_gpu_lm.py -x -q -m gpu > gpurun_out/o1_pytest_lm.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/o1_pytest_lm.log
+echo "== timeline KV=1"; ACB_LM_TIMING=1 timeout 300 python profiles/perf_lm_step.py --one 0 --reps 3 > gpurun_out/o1_timeline_kv1.log 2>&1; tail -11 gpurun_out/o1_timeline_kv1.log
+echo "== perf"; timeout 300 python profiles/perf_lm_step.py > gpurun_out/o1_perf.log 2>&1; cat gpurun_out/o1_perf.log
