@@ -204,26 +204,31 @@ struct GemmParams {
 // CTA = 4 warps, tile = 16 output features x kslice of K.  The CTA's 16 x kslice weight slab is fetched by ONE thread
 // with 16 TMA bulk copies (one per W row, padded pitch => conflict-free fragment reads) BEFORE griddepcontrol.wait, i.e.
 // while the producer of the activations is still running: under PDL the weight stream of kernel n+1 overlaps kernel n.
-template <int NT, int EPI>
+// FT2 = feature tiles of 16 per CTA.  FT2 = 2 (opt-in per GEMM, see pick_ft2) halves the number of CTAs and therefore
+// the activation traffic out of L2: every CTA re-reads the whole 16 x K activation block, and the in-kernel timeline
+// (profiles/r1_lm_timeline_layer0_kv1_fine.log) shows the k-loop of the big GEMMs bound by exactly that (14 MB of
+// activation reads per 14 MB weight matrix; ~0.8 us per dependent batch of loads).
+template <int NT, int EPI, int FT2 = 1>
 __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
     constexpr int U = NT <= 2 ? 4 : (NT <= 4 ? 2 : 1);
     constexpr int RP = 8 * NT + 1;
+    constexpr int FB = 16 * FT2;                     // output features per CTA
     extern __shared__ __align__(128) unsigned char gsm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c4 = lane & 3;
-    const int f0 = blockIdx.x * 16;
+    const int f0 = blockIdx.x * FB;
     const int k0 = blockIdx.y * p.kslice;
     const int ks = min(p.kslice, p.K - k0);          // elements of K this CTA reduces over
     const int pitch = p.kslice * 2 + 64;             // bytes per staged W row (+64: conflict-free LDS.128)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + 16 * pitch);
-    float* red = reinterpret_cast<float*>(gsm + 16 * pitch + 16);   // [4][16][RP]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + FB * pitch);
+    float* red = reinterpret_cast<float*>(gsm + FB * pitch + 16);   // [4][FB][RP]
 
     tl_stamp(p.timing, 0);
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(bar, 16u * (uint32_t)ks * 2u);
+        mbar_expect_tx(bar, (uint32_t)FB * (uint32_t)ks * 2u);
 #pragma unroll 1
-        for (int r = 0; r < 16; ++r)
+        for (int r = 0; r < FB; ++r)
             bulk_g2s(gsm + r * pitch, p.W + (size_t)(f0 + r) * p.K + k0, (uint32_t)ks * 2u, bar);
     }
     pdl_trigger();
@@ -232,9 +237,11 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
     int cache_pos = 0;
     if (EPI == EPI_QKV) cache_pos = p.pos[0];   // requested now, consumed in the epilogue: off the critical path
 
-    float c[NT][4];
+    float c[FT2][NT][4];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+    for (int ft = 0; ft < FT2; ++ft)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) c[ft][j][0] = c[ft][j][1] = c[ft][j][2] = c[ft][j][3] = 0.f;
 
     const int nkb = ks >> 5;
     const int kbw = (nkb + 3) >> 2;
@@ -256,12 +263,15 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (kb + u < kb1) {
-                const uint4 wa = *reinterpret_cast<const uint4*>(wr0 + (kb + u) * 64);
-                const uint4 wb = *reinterpret_cast<const uint4*>(wr1 + (kb + u) * 64);
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    mma16816(c[j], wa.x, wb.x, wa.y, wb.y, xv[u][j].x, xv[u][j].y);
-                    mma16816(c[j], wa.z, wb.z, wa.w, wb.w, xv[u][j].z, xv[u][j].w);
+                for (int ft = 0; ft < FT2; ++ft) {
+                    const uint4 wa = *reinterpret_cast<const uint4*>(wr0 + ft * 16 * pitch + (kb + u) * 64);
+                    const uint4 wb = *reinterpret_cast<const uint4*>(wr1 + ft * 16 * pitch + (kb + u) * 64);
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        mma16816(c[ft][j], wa.x, wb.x, wa.y, wb.y, xv[u][j].x, xv[u][j].y);
+                        mma16816(c[ft][j], wa.z, wb.z, wa.w, wb.w, xv[u][j].z, xv[u][j].w);
+                    }
                 }
             }
         }
@@ -270,20 +280,23 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
     tl_stamp(p.timing, 2);
     // cross-warp (split-K inside the CTA) reduction in a fixed order
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        red[(warp * 16 + g) * RP + 8 * j + 2 * c4] = c[j][0];
-        red[(warp * 16 + g) * RP + 8 * j + 2 * c4 + 1] = c[j][1];
-        red[(warp * 16 + g + 8) * RP + 8 * j + 2 * c4] = c[j][2];
-        red[(warp * 16 + g + 8) * RP + 8 * j + 2 * c4 + 1] = c[j][3];
-    }
+    for (int ft = 0; ft < FT2; ++ft)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            float* r0 = red + (warp * FB + ft * 16 + g) * RP + 8 * j + 2 * c4;
+            r0[0] = c[ft][j][0];
+            r0[1] = c[ft][j][1];
+            r0[8 * RP] = c[ft][j][2];
+            r0[8 * RP + 1] = c[ft][j][3];
+        }
     __syncthreads();
     tl_stamp(p.timing, 5);
-    for (int idx = tid; idx < 16 * 8 * NT; idx += 128) {
-        const int row = idx >> 4, feat = idx & 15;
+    for (int idx = tid; idx < FB * 8 * NT; idx += 128) {
+        const int row = idx / FB, feat = idx % FB;
         if (row >= p.rows) continue;
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) v += red[(w * 16 + feat) * RP + row];
+        for (int w = 0; w < 4; ++w) v += red[(w * FB + feat) * RP + row];
         const int n = f0 + feat;
         if (EPI == EPI_PARTIAL) {
             p.out_f32[blockIdx.y * p.split_stride + (size_t)row * p.ld_out + n] = v;
@@ -291,13 +304,13 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
             p.out_f32[(size_t)row * p.ld_out + n] = v;
         } else if (EPI == EPI_GELU) {
             p.out_f16[(size_t)row * p.ld_out + n] = __float2half_rn(gelu_erf(half_round(v)));
-        } else if (EPI == EPI_QKV) {
-            if (n < p.d) {
-                p.q32[(size_t)row * p.d + n] = v;
+        } else if (EPI == EPI_QKV) {   // q | k | v blocks of d features each (no integer division: cold code costs here)
+            const int which = n >= 2 * p.d ? 2 : (n >= p.d ? 1 : 0), nn = n - which * p.d;
+            if (which == 0) {
+                p.q32[(size_t)row * p.d + nn] = v;
             } else {
-                const int which = (n - p.d) / p.d, nn = n % p.d, h = nn >> 6, dd = nn & 63;
-                __half* cache = which ? p.vc : p.kc;
-                cache[(((size_t)row * p.H + h) * p.cache_len + cache_pos) * 64 + dd] = __float2half_rn(v);
+                __half* cache = which == 2 ? p.vc : p.kc;
+                cache[(((size_t)row * p.H + (nn >> 6)) * p.cache_len + cache_pos) * 64 + (nn & 63)] = __float2half_rn(v);
             }
         } else {  // EPI_CROSSKV: GEMM rows are (row, text position) pairs
             const int R = p.row0 + row, r = R / p.text_len, tc = R % p.text_len;
@@ -1263,36 +1276,64 @@ static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 
 static int nt_for_rows(int rows) { return rows <= 8 ? 1 : (rows <= 16 ? 2 : (rows <= 32 ? 4 : 8)); }
 
-static size_t gemm_smem_bytes(int nt, int kslice) {
-    return (size_t)16 * (kslice * 2 + 64) + 16 + (size_t)4 * 16 * (8 * nt + 1) * sizeof(float);
+static size_t gemm_smem_bytes(int nt, int kslice, int ft2 = 1) {
+    return (size_t)16 * ft2 * (kslice * 2 + 64) + 16 + (size_t)4 * 16 * ft2 * (8 * nt + 1) * sizeof(float);
 }
+constexpr int GEMM_MAX_SMEM = 120 * 1024;
 
-template <int EPI>
-static int launch_gemm(int nt, const GemmParams& p, int nsplit, cudaStream_t s, bool pdl) {
-    dim3 grid(p.N / 16, nsplit);
-    const size_t smem = gemm_smem_bytes(nt, p.kslice);
+template <int EPI, int FT2>
+static int launch_gemm_ft(int nt, const GemmParams& p, int nsplit, cudaStream_t s, bool pdl) {
+    dim3 grid(p.N / (16 * FT2), nsplit);
+    const size_t smem = gemm_smem_bytes(nt, p.kslice, FT2);
+    ACB_REQUIRE(smem <= (size_t)GEMM_MAX_SMEM && p.N % (16 * FT2) == 0, "lm_gemm: tile does not fit (N=%d kslice=%d ft2=%d)", p.N, p.kslice, FT2);
     switch (nt) {
-        case 1: ACB_LAUNCH(lm_gemm_kernel<1, EPI>, grid, dim3(128), smem, s, pdl, p); break;
-        case 2: ACB_LAUNCH(lm_gemm_kernel<2, EPI>, grid, dim3(128), smem, s, pdl, p); break;
-        case 4: ACB_LAUNCH(lm_gemm_kernel<4, EPI>, grid, dim3(128), smem, s, pdl, p); break;
-        default: ACB_LAUNCH(lm_gemm_kernel<8, EPI>, grid, dim3(128), smem, s, pdl, p); break;
+        case 1: ACB_LAUNCH((lm_gemm_kernel<1, EPI, FT2>), grid, dim3(128), smem, s, pdl, p); break;
+        case 2: ACB_LAUNCH((lm_gemm_kernel<2, EPI, FT2>), grid, dim3(128), smem, s, pdl, p); break;
+        case 4: ACB_LAUNCH((lm_gemm_kernel<4, EPI, FT2>), grid, dim3(128), smem, s, pdl, p); break;
+        default: ACB_LAUNCH((lm_gemm_kernel<8, EPI, FT2>), grid, dim3(128), smem, s, pdl, p); break;
     }
     return ACB_OK;
 }
+template <int EPI>
+static int launch_gemm(int nt, const GemmParams& p, int nsplit, cudaStream_t s, bool pdl, int ft2 = 1) {
+    if (ft2 == 2) {
+        if constexpr (EPI == EPI_CROSSKV) { acb_set_error("lm_gemm: the cross-K/V prefill uses 16-feature tiles"); return ACB_ERR_INVALID; }
+        else return launch_gemm_ft<EPI, 2>(nt, p, nsplit, s, pdl);
+    }
+    return launch_gemm_ft<EPI, 1>(nt, p, nsplit, s, pdl);
+}
 
-template <int NT, int EPI>
+template <int NT, int EPI, int FT2>
 static cudaError_t gemm_attr_one() {
-    cudaError_t e = cudaFuncSetAttribute(lm_gemm_kernel<NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(lm_gemm_kernel<NT, EPI, FT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_MAX_SMEM);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lm_gemm_kernel<NT, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return cudaFuncSetAttribute(lm_gemm_kernel<NT, EPI, FT2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }
 template <int EPI>
 static cudaError_t gemm_attr_all() {
     cudaError_t e;
-    if ((e = gemm_attr_one<1, EPI>()) != cudaSuccess) return e;
-    if ((e = gemm_attr_one<2, EPI>()) != cudaSuccess) return e;
-    if ((e = gemm_attr_one<4, EPI>()) != cudaSuccess) return e;
-    return gemm_attr_one<8, EPI>();
+    if ((e = gemm_attr_one<1, EPI, 1>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_one<2, EPI, 1>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_one<4, EPI, 1>()) != cudaSuccess) return e;
+    if ((e = gemm_attr_one<8, EPI, 1>()) != cudaSuccess) return e;
+    if constexpr (EPI != EPI_CROSSKV) {
+        if ((e = gemm_attr_one<1, EPI, 2>()) != cudaSuccess) return e;
+        if ((e = gemm_attr_one<2, EPI, 2>()) != cudaSuccess) return e;
+        if ((e = gemm_attr_one<4, EPI, 2>()) != cudaSuccess) return e;
+        if ((e = gemm_attr_one<8, EPI, 2>()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// 32-feature tiles for a GEMM?  Only the big ones (their k-loop is bound by activation re-reads), only when the grid
+// still covers ~90 % of the SMs and the 32-row weight slab fits.  ACB_LM_FT32=0 turns it off.
+static int pick_ft2(int N, int K, int nsplit, int kslice, int nt, int sms) {
+    const char* e = getenv("ACB_LM_FT32");
+    const bool enabled = !(e && e[0] == '0');
+    if (!enabled || N % 32 != 0 || (size_t)N * K < ((size_t)4 << 20)) return 1;
+    if ((N / 32) * nsplit * 10 < sms * 9) return 1;
+    if (gemm_smem_bytes(nt, kslice, 2) > (size_t)GEMM_MAX_SMEM) return 1;
+    return 2;
 }
 
 // K-slices per GEMM: the slab a CTA stages (16 x kslice fp16) must fit ~64 KB of shared memory, and when the
@@ -1506,8 +1547,9 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         const int ns = pick_split(N, K, lm->sms, true, &ks);
         GemmParams p = base_gemm(W, X, N, K, rows, ks);
         p.out_f32 = B.part; p.ld_out = N; p.split_stride = part_stride;
-        p.timing = tl(id == G_O ? "gemm_O" : (id == G_CQ ? "gemm_CQ" : (id == G_CO ? "gemm_CO" : "gemm_FFN2")), layer, (N / 16) * ns);
-        ACB_TRY(launch_gemm<EPI_PARTIAL>(nt, p, ns, s, pdl));
+        const int ft2 = pick_ft2(N, K, ns, ks, nt, lm->sms);
+        p.timing = tl(id == G_O ? "gemm_O" : (id == G_CQ ? "gemm_CQ" : (id == G_CO ? "gemm_CO" : "gemm_FFN2")), layer, (N / (16 * ft2)) * ns);
+        ACB_TRY(launch_gemm<EPI_PARTIAL>(nt, p, ns, s, pdl, ft2));
         ++nl;
         DBG("gemm_EPI_PARTIAL", layer);
         pending = ns;
@@ -1522,8 +1564,9 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             GemmParams p = base_gemm((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, B.h16, 3 * d, d, rows, ks);
             p.q32 = B.q32; p.kc = (__half*)B.k_cache + l * kv_layer; p.vc = (__half*)B.v_cache + l * kv_layer;
             p.d = d; p.H = H; p.cache_len = c.max_seq; p.pos = B.pos;
-            p.timing = tl("gemm_QKV", l, 3 * d / 16);
-            ACB_TRY(launch_gemm<EPI_QKV>(nt, p, 1, s, pdl)); ++nl;
+            const int ft2 = pick_ft2(3 * d, d, 1, ks, nt, lm->sms);
+            p.timing = tl("gemm_QKV", l, 3 * d / (16 * ft2));
+            ACB_TRY(launch_gemm<EPI_QKV>(nt, p, 1, s, pdl, ft2)); ++nl;
             DBG("gemm_EPI_QKV", l);
         }
         if (!gemms_only) {
@@ -1558,8 +1601,9 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             pick_split(ffn, d, lm->sms, false, &ks);
             GemmParams p = base_gemm((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, B.h16, ffn, d, rows, ks);
             p.out_f16 = (__half*)B.f16; p.ld_out = ffn;
-            p.timing = tl("gemm_FFN1", l, ffn / 16);
-            ACB_TRY(launch_gemm<EPI_GELU>(nt, p, 1, s, pdl)); ++nl;
+            const int ft2 = pick_ft2(ffn, d, 1, ks, nt, lm->sms);
+            p.timing = tl("gemm_FFN1", l, ffn / (16 * ft2));
+            ACB_TRY(launch_gemm<EPI_GELU>(nt, p, 1, s, pdl, ft2)); ++nl;
             DBG("gemm_EPI_GELU", l);
         }
         ACB_TRY(partial_gemm((const __half*)lm->w.w_ff2 + (size_t)l * d * ffn, B.f16, d, ffn, l, G_FF2));
@@ -1570,7 +1614,7 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         pick_split(N, d, lm->sms, false, &ks);
         GemmParams p = base_gemm(lm->w.heads, B.h16, N, d, rows, ks);
         p.out_f32 = B.logits; p.ld_out = N;
-        ACB_TRY(launch_gemm<EPI_F32>(nt, p, 1, s, pdl)); ++nl;
+        ACB_TRY(launch_gemm<EPI_F32>(nt, p, 1, s, pdl, pick_ft2(N, d, 1, ks, nt, lm->sms))); ++nl;
         DBG("gemm_EPI_F32", -1);
     }
     if (!gemms_only) {

@@ -258,10 +258,29 @@ def test_wide_step_matches_default_kernels(monkeypatch, name, B, env):
     assert (out == ref).float().mean() > 0.9
 
 
-@pytest.mark.parametrize('name,B', [('lm_medium_2l', 8), ('lm_large_2l', 4), ('lm_large_2l', 32)])
-def test_released_widths_match_oracle(name, B):
+@pytest.mark.parametrize('name,B', [('lm_medium_2l', 8), ('lm_large_2l', 4), ('lm_medium_2l', 2)])
+def test_ft32_tiles_equal_16_feature_tiles(monkeypatch, name, B):
+    """The big decode GEMMs (QKV, FFN1, FFN2, heads at d = 1536; FFN2 at d = 2048) use 32-feature tiles by default
+    (half the CTAs, half the activation re-reads out of L2); ACB_LM_FT32=0 forces the 16-feature tiles everywhere.  The
+    K-split and the per-element summation order are the same, so the logits must be bit-identical."""
+    cfg, sd, m = _model(name, 7)
+    T = 5
+    _, _, cross = H.lm_condition(cfg, sd, B, 6, 2)
+    seq = torch.randint(0, cfg['card'], (B, 4, T + 4), generator=torch.Generator().manual_seed(3))
+    wide = m.teacher_forced_logits(seq, cross, 3.0).cpu()
+    monkeypatch.setenv('ACB_LM_FT32', '0')
+    narrow = m.teacher_forced_logits(seq, cross, 3.0).cpu()
+    monkeypatch.delenv('ACB_LM_FT32')
+    assert torch.isfinite(wide).all()
+    assert torch.equal(wide, narrow), f'max diff {(wide - narrow).abs().max():.3e}'
+
+
+@pytest.mark.parametrize('name,B,ft32', [('lm_medium_2l', 8, '1'), ('lm_medium_2l', 8, '0'), ('lm_large_2l', 4, '1'),
+                                         ('lm_large_2l', 32, '1')])
+def test_released_widths_match_oracle(monkeypatch, name, B, ft32):
     """MusicGen-medium / -large layer shapes (d = 1536 / 2048, 4d FFN, card 2048) at bench-like row counts
     (rows = 16, 8 and 64 = BASELINE config 5 on one GPU), two layers deep: CFG-mixed logits vs the fp16-emulating oracle."""
+    monkeypatch.setenv('ACB_LM_FT32', ft32)   # 32-feature GEMM tiles (default) / 16-feature tiles only
     cfg, sd, m = _model(name, 11)
     _, _, cross = H.lm_condition(cfg, sd, B, 7, 3)
     T = 4
