@@ -654,11 +654,17 @@ struct AttnParams {
     const __half* kc; const __half* vc; __half* out;
     int H, d, cache_len; const int* pos; int fixed_len; float scale;
     unsigned long long* timing;   // debug timeline
+    float* part; int* counter;    // split-KV self attention (gridDim.z > 1): partial (m, l, acc[64]) records, arrival counters
 };
 
-// Self attention for one query token: CTA = (row, head), 8 warps, ONE pass over K and V with an online softmax.
+// Self attention for one query token: CTA = (row, head[, KV third]), 8 warps, ONE pass over K and V with an online softmax.
 // A warp instruction reads 4 consecutive cache positions (4 x 128 B = 512 contiguous bytes); 8 lanes share a position
 // (8 dims each).  4 positions-groups x 4 unrolled iterations of K and V are in flight per lane before any is consumed.
+// Split KV (gridDim.z = 3): rows x heads = 384 CTAs are 2.6 per SM, so SMs holding 3 finish ~25 % after those holding 2
+// (timeline at KV 751: median CTA 16.7 us, last 22.3 us).  Once the context is longer than 128 positions it is cut into
+// up to 3 chunks (multiples of the CTA's 128-position stride): 1 152 CTAs = 7.8 per SM.  Every chunk CTA writes its
+// (m, l, acc) record, and the LAST one to arrive (atomic counter, threadfence) merges the records in chunk order, so the
+// result does not depend on arrival order.  Short contexts take the single-CTA path; the idle CTAs exit at once.
 constexpr int ATT_WARPS = 8, ATT_UNROLL = 4;   // UNROLL 8 measured slower (98 regs: 2 CTAs/SM instead of 5)
 
 struct OnlineSM { float m, l, acc[8]; };
@@ -680,6 +686,14 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     pdl_wait();
     tl_stamp(p.timing, 1);
     const int n = p.fixed_len > 0 ? p.fixed_len : p.pos[0] + 1;
+    int lo = 0, hi = n, nact = 1;
+    if (gridDim.z > 1) {
+        const int S = gridDim.z, chunk = max(128, ((n + S - 1) / S + 127) & ~127);
+        nact = (n + chunk - 1) / chunk;
+        if ((int)blockIdx.z >= nact) return;         // CTA-uniform: nothing in this chunk
+        lo = blockIdx.z * chunk;
+        hi = min(n, lo + chunk);
+    }
 
     float q[8];
     {   // (split-K query partials exist only on the cross-attention path; a rolled/unrolled split loop here cost
@@ -701,12 +715,12 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     for (int e = 0; e < 8; ++e) st.acc[e] = 0.f;
 
     // warp-uniform loop bound (the shuffles need all 32 lanes)
-    for (int pb = warp * 4; pb < n; pb += ATT_WARPS * 4 * ATT_UNROLL) {
+    for (int pb = lo + warp * 4; pb < hi; pb += ATT_WARPS * 4 * ATT_UNROLL) {
         uint4 kv[ATT_UNROLL], vv[ATT_UNROLL];
 #pragma unroll
         for (int u = 0; u < ATT_UNROLL; ++u) {
             const int pp = pb + u * ATT_WARPS * 4 + pg;
-            if (pp < n) {
+            if (pp < hi) {
                 kv[u] = ld_stream_u4(kb + (size_t)pp * 64);
                 vv[u] = ld_stream_u4(vb + (size_t)pp * 64);
             } else {
@@ -727,7 +741,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             s += __shfl_xor_sync(0xffffffffu, s, 4);
-            if (pp < n) {
+            if (pp < hi) {
                 const float mn = fmaxf(st.m, s);
                 const float corr = __expf(st.m - mn);   // exp(-inf) = 0 on the first position
                 const float pw = __expf(s - mn);
@@ -761,18 +775,46 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     }
     __syncthreads();
     tl_stamp(p.timing, 6);
+    float mx = -INFINITY, l = 0.f, o = 0.f;
     if (tid < 64) {
-        float mx = wm[0];
+        mx = wm[0];
 #pragma unroll
         for (int w = 1; w < ATT_WARPS; ++w) mx = fmaxf(mx, wm[w]);
-        float l = 0.f, o = 0.f;
 #pragma unroll
         for (int w = 0; w < ATT_WARPS; ++w) {
             const float cw = wm[w] == -INFINITY ? 0.f : __expf(wm[w] - mx);
             l = fmaf(wl[w], cw, l);
             o = fmaf(wacc[w][tid], cw, o);
         }
-        p.out[(size_t)row * p.d + h * 64 + tid] = __float2half_rn(o / l);
+    }
+    if (nact == 1) {                                 // CTA-uniform
+        if (tid < 64) p.out[(size_t)row * p.d + h * 64 + tid] = __float2half_rn(o / l);
+    } else {
+        __shared__ int is_last;
+        float* rec = p.part + ((size_t)row * p.H + h) * gridDim.z * 66;
+        if (tid < 64) {
+            rec[blockIdx.z * 66 + 2 + tid] = o;
+            if (tid == 0) { rec[blockIdx.z * 66] = mx; rec[blockIdx.z * 66 + 1] = l; }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last = atomicAdd(p.counter + row * p.H + h, 1) == nact - 1;
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            if (tid < 64) {
+                float M = -INFINITY;
+                for (int z = 0; z < nact; ++z) M = fmaxf(M, __ldcg(rec + z * 66));
+                float L = 0.f, O = 0.f;
+                for (int z = 0; z < nact; ++z) {     // chunk order: independent of which CTA arrived last
+                    const float cz = __expf(__ldcg(rec + z * 66) - M);
+                    L = fmaf(__ldcg(rec + z * 66 + 1), cz, L);
+                    O = fmaf(__ldcg(rec + z * 66 + 2 + tid), cz, O);
+                }
+                p.out[(size_t)row * p.d + h * 64 + tid] = __float2half_rn(O / L);
+            }
+            if (tid == 0) p.counter[row * p.H + h] = 0;   // ready for the next layer / step
+        }
     }
     tl_stamp(p.timing, 3);
 }
@@ -1524,6 +1566,12 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
     //  built and measured: 2.240 vs 2.258 ms per step, i.e. nothing: under PDL the weight slab is already in flight before
     //  the dependency resolves, weights are not on the critical path.  profiles/r1_perf_step_v5_l2prefetch_no_gain.log)
     enum { G_QKV, G_O, G_CQ, G_CO, G_FF1, G_FF2, G_HEADS };
+    // split-KV self attention: records and counters live in the (otherwise chain-mode-only) plan buffer
+    int att_split = env_int("ACB_LM_ATT_SPLIT", 3);
+    if (att_split < 1 || att_split > 8 || !B.plan ||
+        ACB_PLAN_COUNTER_BYTES + (size_t)rows * H * att_split * 66 * sizeof(float) > ACB_LM_PLAN_BYTES ||
+        (size_t)rows * H * sizeof(int) > ACB_PLAN_COUNTER_BYTES)
+        att_split = 1;
     // debug timeline (ACB_LM_TIMING=1): every kernel of layer 0 of a directly enqueued step gets a stamp buffer
     if (lm->timing && !capturing) lm->timed.clear();
     auto tl = [&](const char* what, int layer, int ctas) -> unsigned long long* {
@@ -1572,8 +1620,10 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         if (!gemms_only) {
             AttnParams a{B.q32, 1, 0, (__half*)B.k_cache + l * kv_layer, (__half*)B.v_cache + l * kv_layer, (__half*)B.a16,
                          H, d, c.max_seq, B.pos, 0, scale};
-            a.timing = tl("attn", l, H * rows);
-            ACB_LAUNCH(lm_attn_kernel, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            a.timing = tl("attn", l, H * rows * att_split);
+            a.part = reinterpret_cast<float*>((unsigned char*)B.plan + ACB_PLAN_COUNTER_BYTES);
+            a.counter = reinterpret_cast<int*>(B.plan);
+            ACB_LAUNCH(lm_attn_kernel, dim3(H, rows, att_split), dim3(ATT_WARPS * 32), 0, s, pdl, a);
             ++nl;
             DBG("lm_attn_kernel", l);
         }
@@ -2004,6 +2054,7 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
         const char* ec = getenv("ACB_LM_CHAIN");
         lm->chain = (ec && ec[0] == '1') && lm->buf.plan != nullptr;
         if (lm->chain) ACB_TRY(build_chain_plan(lm, s));
+        else if (lm->buf.plan) ACB_CHECK_CUDA(cudaMemsetAsync(lm->buf.plan, 0, ACB_PLAN_COUNTER_BYTES, s));   // split-KV arrival counters
     }
     for (int attempt = 0; attempt < 2; ++attempt) {
         drop_graph(lm);

@@ -258,6 +258,35 @@ def test_wide_step_matches_default_kernels(monkeypatch, name, B, env):
     assert (out == ref).float().mean() > 0.9
 
 
+def test_long_context_split_kv_attention(monkeypatch):
+    """Beyond 128 cached positions self attention is cut into up to three KV chunks per (row, head); the last chunk CTA
+    to arrive merges the (m, l, acc) records in chunk order.  420 teacher-forced steps (chunk layouts 1 -> 2 -> 3 and
+    the 256-wide chunks after position 384): against the single-CTA path (ACB_LM_ATT_SPLIT=1) and the oracle."""
+    cfg, sd, m = _model('lm_mini', 9)
+    B, T = 2, 420
+    _, _, cross = H.lm_condition(cfg, sd, B, 5, 4)
+    seq = torch.randint(0, cfg['card'], (B, 4, T + 4), generator=torch.Generator().manual_seed(5))
+    o = LO.LMOracle(sd, cfg, half_gemm=True)
+    rec = []
+    o.generate(None, cross, B, T, use_sampling=False, record_logits=rec, teacher=seq)
+    ref = torch.stack(rec)
+    split = m.teacher_forced_logits(o.last_sequence, cross, cfg['cfg_coef']).cpu()
+    monkeypatch.setenv('ACB_LM_ATT_SPLIT', '1')
+    single = m.teacher_forced_logits(o.last_sequence, cross, cfg['cfg_coef']).cpu()
+    monkeypatch.delenv('ACB_LM_ATT_SPLIT')
+    n = ref.shape[0]
+    print(f'split-KV: max |split - single| {(split - single).abs().max():.2e}, max |split - oracle| '
+          f'{(split[:n] - ref).abs().max():.2e} on |logits| <= {ref.abs().max():.1f}')
+    assert torch.isfinite(split).all()
+    torch.testing.assert_close(split, single, rtol=0, atol=3e-2)
+    torch.testing.assert_close(split[:n], ref, rtol=2e-2, atol=3e-2)
+    # the graph-replayed generation takes the same path
+    out = m.generate(None, [], num_samples=B, max_gen_len=300, use_sampling=False, cross_attention_src=cross).cpu()
+    monkeypatch.setenv('ACB_LM_ATT_SPLIT', '1')
+    out1 = m.generate(None, [], num_samples=B, max_gen_len=300, use_sampling=False, cross_attention_src=cross).cpu()
+    assert (out == out1).float().mean() > 0.9
+
+
 @pytest.mark.parametrize('name,B', [('lm_medium_2l', 8), ('lm_large_2l', 4), ('lm_medium_2l', 2)])
 def test_ft32_tiles_equal_16_feature_tiles(monkeypatch, name, B):
     """The big decode GEMMs (QKV, FFN1, FFN2, heads at d = 1536; FFN2 at d = 2048) use 32-feature tiles by default
