@@ -655,13 +655,14 @@ struct AttnParams {
     int H, d, cache_len; const int* pos; int fixed_len; float scale;
     unsigned long long* timing;   // debug timeline
     float* part; int* counter;    // split-KV self attention (gridDim.z > 1): partial (m, l, acc[64]) records, arrival counters
+    int split_min;                // contexts shorter than this stay on the single-CTA path
 };
 
 // Self attention for one query token: CTA = (row, head[, KV third]), 8 warps, ONE pass over K and V with an online softmax.
 // A warp instruction reads 4 consecutive cache positions (4 x 128 B = 512 contiguous bytes); 8 lanes share a position
 // (8 dims each).  4 positions-groups x 4 unrolled iterations of K and V are in flight per lane before any is consumed.
 // Split KV (gridDim.z = 3): rows x heads = 384 CTAs are 2.6 per SM, so SMs holding 3 finish ~25 % after those holding 2
-// (timeline at KV 751: median CTA 16.7 us, last 22.3 us).  Once the context is longer than 128 positions it is cut into
+// (timeline at KV 751: median CTA 16.7 us, last 22.3 us).  Once the context reaches split_min positions it is cut into
 // up to 3 chunks (multiples of the CTA's 128-position stride): 1 152 CTAs = 7.8 per SM.  Every chunk CTA writes its
 // (m, l, acc) record, and the LAST one to arrive (atomic counter, threadfence) merges the records in chunk order, so the
 // result does not depend on arrival order.  Short contexts take the single-CTA path; the idle CTAs exit at once.
@@ -688,7 +689,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     const int n = p.fixed_len > 0 ? p.fixed_len : p.pos[0] + 1;
     int lo = 0, hi = n, nact = 1;
     if (gridDim.z > 1) {
-        const int S = gridDim.z, chunk = max(128, ((n + S - 1) / S + 127) & ~127);
+        // measured: the record write + atomic + merge costs more than the balance gains below ~750 positions
+        // (KV 376: 2.71 vs 2.57 ms per step; KV 751: equal; KV 1500: 3.62 vs 3.80), hence split_min (default 768)
+        const int S = gridDim.z, chunk = n < p.split_min ? n : max(128, ((n + S - 1) / S + 127) & ~127);
         nact = (n + chunk - 1) / chunk;
         if ((int)blockIdx.z >= nact) return;         // CTA-uniform: nothing in this chunk
         lo = blockIdx.z * chunk;
@@ -1623,6 +1626,7 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             a.timing = tl("attn", l, H * rows * att_split);
             a.part = reinterpret_cast<float*>((unsigned char*)B.plan + ACB_PLAN_COUNTER_BYTES);
             a.counter = reinterpret_cast<int*>(B.plan);
+            a.split_min = max(129, env_int("ACB_LM_ATT_SPLIT_MIN", 768));
             ACB_LAUNCH(lm_attn_kernel, dim3(H, rows, att_split), dim3(ATT_WARPS * 32), 0, s, pdl, a);
             ++nl;
             DBG("lm_attn_kernel", l);

@@ -259,9 +259,11 @@ def test_wide_step_matches_default_kernels(monkeypatch, name, B, env):
 
 
 def test_long_context_split_kv_attention(monkeypatch):
-    """Beyond 128 cached positions self attention is cut into up to three KV chunks per (row, head); the last chunk CTA
-    to arrive merges the (m, l, acc) records in chunk order.  420 teacher-forced steps (chunk layouts 1 -> 2 -> 3 and
-    the 256-wide chunks after position 384): against the single-CTA path (ACB_LM_ATT_SPLIT=1) and the oracle."""
+    """Long contexts (>= ACB_LM_ATT_SPLIT_MIN positions, default 768; 129 here) cut self attention into up to three KV
+    chunks per (row, head); the last chunk CTA to arrive merges the (m, l, acc) records in chunk order.  420
+    teacher-forced steps (chunk layouts 1 -> 2 -> 3 and the 256-wide chunks after position 384): against the single-CTA
+    path (ACB_LM_ATT_SPLIT=1) and the oracle."""
+    monkeypatch.setenv('ACB_LM_ATT_SPLIT_MIN', '129')   # default 768: split from the first eligible length here
     cfg, sd, m = _model('lm_mini', 9)
     B, T = 2, 420
     _, _, cross = H.lm_condition(cfg, sd, B, 5, 4)
