@@ -661,7 +661,7 @@ struct AttnParams {
 // Self attention for one query token: CTA = (row, head[, KV third]), 8 warps, ONE pass over K and V with an online softmax.
 // A warp instruction reads 4 consecutive cache positions (4 x 128 B = 512 contiguous bytes); 8 lanes share a position
 // (8 dims each).  4 positions-groups x 4 unrolled iterations of K and V are in flight per lane before any is consumed.
-// Split KV (gridDim.z = 3): rows x heads = 384 CTAs are 2.6 per SM, so SMs holding 3 finish ~25 % after those holding 2
+// Split KV (gridDim.z = 3, opt-in: ACB_LM_ATT_SPLIT=3): rows x heads = 384 CTAs are 2.6 per SM, so SMs holding 3 finish ~25 % after those holding 2
 // (timeline at KV 751: median CTA 16.7 us, last 22.3 us).  Once the context reaches split_min positions it is cut into
 // up to 3 chunks (multiples of the CTA's 128-position stride): 1 152 CTAs = 7.8 per SM.  Every chunk CTA writes its
 // (m, l, acc) record, and the LAST one to arrive (atomic counter, threadfence) merges the records in chunk order, so the
@@ -1570,7 +1570,10 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
     //  the dependency resolves, weights are not on the critical path.  profiles/r1_perf_step_v5_l2prefetch_no_gain.log)
     enum { G_QKV, G_O, G_CQ, G_CO, G_FF1, G_FF2, G_HEADS };
     // split-KV self attention: records and counters live in the (otherwise chain-mode-only) plan buffer
-    int att_split = env_int("ACB_LM_ATT_SPLIT", 3);
+    // OFF by default (ACB_LM_ATT_SPLIT=3 enables): measured on the 30 s workload it gains 2.8 % per step at KV 1500 and
+    // 0.5 % at 1126 but the 768 extra (idle) CTAs per launch and the larger kernel cost 1-4 % per step below ~800
+    // positions -- 53.0 vs 54.1 audio-s/s over the whole generation (profiles/r1_perf_step_v8_splitkv_*.log).
+    int att_split = env_int("ACB_LM_ATT_SPLIT", 1);
     if (att_split < 1 || att_split > 8 || !B.plan ||
         ACB_PLAN_COUNTER_BYTES + (size_t)rows * H * att_split * 66 * sizeof(float) > ACB_LM_PLAN_BYTES ||
         (size_t)rows * H * sizeof(int) > ACB_PLAN_COUNTER_BYTES)
