@@ -678,6 +678,7 @@ __device__ __forceinline__ void osm_merge(OnlineSM& a, float m2, float l2, const
     a.m = mn;
 }
 
+template <bool SPLIT>   // SPLIT = false (default step): none of the chunk / record / merge code is compiled in
 __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     __shared__ float wm[ATT_WARPS], wl[ATT_WARPS], wacc[ATT_WARPS][64];
     const int h = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -688,7 +689,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     tl_stamp(p.timing, 1);
     const int n = p.fixed_len > 0 ? p.fixed_len : p.pos[0] + 1;
     int lo = 0, hi = n, nact = 1;
-    if (gridDim.z > 1) {
+    if (SPLIT && gridDim.z > 1) {
         // measured: the record write + atomic + merge costs more than the balance gains below ~750 positions
         // (KV 376: 2.71 vs 2.57 ms per step; KV 751: equal; KV 1500: 3.62 vs 3.80), hence split_min (default 768)
         const int S = gridDim.z, chunk = n < p.split_min ? n : max(128, ((n + S - 1) / S + 127) & ~127);
@@ -790,7 +791,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
             o = fmaf(wacc[w][tid], cw, o);
         }
     }
-    if (nact == 1) {                                 // CTA-uniform
+    if (!SPLIT || nact == 1) {                       // CTA-uniform
         if (tid < 64) p.out[(size_t)row * p.d + h * 64 + tid] = __float2half_rn(o / l);
     } else {
         __shared__ int is_last;
@@ -962,7 +963,43 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
         for (int i = tid; i < card; i += nt) pr[i] = pr[i] / s;
         __syncthreads();
         const int kk = p.top_k > card ? card : p.top_k;
-        if (p.top_p > 0.f || kk > 0) {
+        if (p.top_p <= 0.f && kk > 0) {
+            // utils.sample_top_k (utils/utils.py:108-122) keeps p >= the k-th largest probability and renormalises: only
+            // that VALUE is needed, so instead of sorting (66 block barriers for 2048 candidates) select it exactly with
+            // a 4-pass radix select on the bit patterns (non-negative floats order like their uint32 bits).
+            __shared__ int hist[256];
+            __shared__ int s_bin, s_rem;
+            uint32_t prefix = 0u, mask = 0u;
+            int remaining = kk;                     // rank (from the top) among the candidates matching prefix/mask
+#pragma unroll 1
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                for (int i = tid; i < 256; i += nt) hist[i] = 0;
+                __syncthreads();
+                for (int i = tid; i < card; i += nt) {
+                    const uint32_t key = __float_as_uint(pr[i]);
+                    if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int acc = 0, bin = 255;
+                    for (; bin > 0; --bin) {
+                        if (acc + hist[bin] >= remaining) break;
+                        acc += hist[bin];
+                    }
+                    s_bin = bin; s_rem = remaining - acc;
+                }
+                __syncthreads();
+                prefix |= (uint32_t)s_bin << shift;
+                mask |= 255u << shift;
+                remaining = s_rem;
+            }
+            const float kth = __uint_as_float(prefix);
+            float ls2 = 0.f;
+            for (int i = tid; i < card; i += nt) { float v = pr[i] >= kth ? pr[i] : 0.f; pr[i] = v; ls2 += v; }
+            const float s2 = block_sum(ls2, red[2]);
+            for (int i = tid; i < card; i += nt) pr[i] = pr[i] / s2;
+            __syncthreads();
+        } else if (p.top_p > 0.f || kk > 0) {
             for (int i = tid; i < p.NP; i += nt) { sv[i] = i < card ? pr[i] : -INFINITY; si[i] = i; }
             __syncthreads();
             for (int size = 2; size <= p.NP; size <<= 1)
@@ -1375,7 +1412,7 @@ static cudaError_t gemm_attr_all() {
 static int pick_ft2(int N, int K, int nsplit, int kslice, int nt, int sms) {
     const char* e = getenv("ACB_LM_FT32");
     const bool enabled = !(e && e[0] == '0');
-    if (!enabled || N % 32 != 0 || (size_t)N * K < ((size_t)4 << 20)) return 1;
+    if (!enabled || N % 32 != 0 || (size_t)N * K < ((size_t)2 << 20)) return 1;   // d x d at d = 1536 qualifies (2.36 M weights)
     if ((N / 32) * nsplit * 10 < sms * 9) return 1;
     if (gemm_smem_bytes(nt, kslice, 2) > (size_t)GEMM_MAX_SMEM) return 1;
     return 2;
@@ -1630,7 +1667,8 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             a.part = reinterpret_cast<float*>((unsigned char*)B.plan + ACB_PLAN_COUNTER_BYTES);
             a.counter = reinterpret_cast<int*>(B.plan);
             a.split_min = max(129, env_int("ACB_LM_ATT_SPLIT_MIN", 768));
-            ACB_LAUNCH(lm_attn_kernel, dim3(H, rows, att_split), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            if (att_split > 1) ACB_LAUNCH(lm_attn_kernel<true>, dim3(H, rows, att_split), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            else ACB_LAUNCH(lm_attn_kernel<false>, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
             ++nl;
             DBG("lm_attn_kernel", l);
         }
@@ -1823,7 +1861,7 @@ static int enqueue_step_wide(acb_lm* lm, cudaStream_t s, float* logits_out, int*
         if (!gemms_only) {
             AttnParams a{B.q32, 1, 0, (__half*)B.k_cache + l * kv_layer, (__half*)B.v_cache + l * kv_layer, (__half*)B.a16,
                          H, d, c.max_seq, B.pos, 0, scale};
-            ACB_LAUNCH(lm_attn_kernel, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            ACB_LAUNCH(lm_attn_kernel<false>, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
             ++nl;
             DBG("lm_attn_kernel", l);
         }
@@ -1905,7 +1943,7 @@ static int enqueue_step_chain(acb_lm* lm, cudaStream_t s, float* logits_out, int
         if (!chains_only) {
             AttnParams a{B.q32, 1, 0, (__half*)B.k_cache + l * kv_layer, (__half*)B.v_cache + l * kv_layer, (__half*)B.a16,
                          H, d, c.max_seq, B.pos, 0, scale};
-            ACB_LAUNCH(lm_attn_kernel, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            ACB_LAUNCH(lm_attn_kernel<false>, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
             ++nl;
             DBG("lm_attn_kernel", l);
         }
@@ -1972,7 +2010,8 @@ extern "C" int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, 
     if (ea == cudaSuccess) ea = gemm_attr_all<EPI_GELU>();
     if (ea == cudaSuccess) ea = gemm_attr_all<EPI_F32>();
     if (ea == cudaSuccess) ea = gemm_attr_all<EPI_CROSSKV>();
-    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_cross_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_ln_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_embed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
