@@ -207,7 +207,7 @@ def run_b200(args):
     gemm_ms = e0.elapsed_time(e1) / reps
     pk = peaks()
     traffic = None   # dram__bytes_read+write of lm_gemm_kernel over one step, from the committed ncu capture
-    tp = os.path.join(ROOT, 'profiles', 'r1_step_kv750_v3_dram_summary.json')
+    tp = os.path.join(ROOT, 'profiles', 'r1_step_kv750_v9_dram_summary.json')   # ncu capture of the current kernels
     if os.path.exists(tp) and args.scale == 'medium' and B == 8:
         tj = json.load(open(tp)).get('lm_gemm_kernel')
         if tj:
