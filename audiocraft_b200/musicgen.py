@@ -18,6 +18,7 @@ import typing as tp
 
 import torch
 
+from .audio_utils import convert_audio
 from .conditioners import ConditioningAttributes
 from .encodec import CompressionModel
 from .lm import LMModel
@@ -62,10 +63,8 @@ class BaseGenModel:
             prompt = prompt[None]
         if prompt.dim() != 3:
             raise ValueError("prompt should have 3 dimensions: [B, C, T] (C = 1).")
-        if prompt_sample_rate != self.sample_rate or prompt.shape[1] != self.audio_channels:
-            # the reference resamples / remixes with julius here (data/audio_utils.py:54-59): host IO, not built
-            raise NotImplementedError(f"convert_audio is not built: pass the prompt at {self.sample_rate} Hz with "
-                                      f"{self.audio_channels} channel(s)")
+        # resample / remix like the reference (genmodel.py:183 -> data/audio_utils.py:54-59); host-side, once per call
+        prompt = convert_audio(prompt, prompt_sample_rate, self.sample_rate, self.audio_channels)
         if descriptions is None:
             descriptions = [None] * len(prompt)
         return self._run(descriptions, prompt, progress, return_tokens)

@@ -204,6 +204,10 @@ def test_musicgen_api_shapes_and_callbacks():
     x = H.audio_input(cm.cfg, 2, 8000, 1)
     wav, tok = mg.generate_continuation(x, 16000, ['x', None], return_tokens=True)
     assert tok.shape[-1] == int(1.0 * fr)
+    # a stereo prompt at another rate goes through convert_audio (resample + downmix) like genmodel.py:183
+    x8 = H.audio_input(cm.cfg, 2, 8000 * cm.sample_rate // 16000 // 2, 1)
+    wav, tok = mg.generate_continuation(torch.cat([x8, 0.5 * x8], dim=1), cm.sample_rate // 2, ['x', None], return_tokens=True)
+    assert tok.shape[-1] == int(1.0 * fr)
     mg.set_generation_params(duration=3.0, extend_stride=1.0)
     wav, tok = mg.generate(['long one'], return_tokens=True)
     assert tok.shape == (1, 4, int(3.0 * fr))
