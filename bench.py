@@ -275,7 +275,7 @@ def run_b200(args):
                     e2e=dict(value=round(e2e_value, 2), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes),
                     gpu_launches=(lm.launches_per_step * (S - 1) + dec_launches) * args.steps,
                     roofline=roofline, cpu_baseline=cpu_baseline, secondary=secondary)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -331,10 +331,31 @@ def run_reference(args):
                 config=dict(workload=f'MusicGen-{args.scale} text-conditioned {args.duration:g}s generation, batch={args.batch} '
                                      f'(CFG rows={2 * args.batch}); bounded sample, see cpu_baseline.sample'),
                 cpu_baseline=cb, e2e=dict(value=cb['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to stdout when
+    the box sets NCCL_DEBUG): keep a private handle on the real stdout for the result and point fd 1 at stderr for
+    everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 if __name__ == '__main__':
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
