@@ -56,6 +56,8 @@ def lib():
     L.acb_weight_norm_fold.argtypes = [vp, vp, vp, ci, ci, vp]
     L.acb_conv1d.argtypes = [vp, vp, vp, vp, vp] + [ci] * 13 + [vp]
     L.acb_convtr1d.argtypes = [vp, vp, vp, vp, vp] + [ci] * 10 + [vp]
+    L.acb_conv1d_t6.argtypes = [vp, vp, vp, vp, vp] + [ci] * 12 + [vp]
+    L.acb_conv1d_t6_tile.argtypes = [ci]
     L.acb_lstm_recurrent.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
     L.acb_lstm_state_bytes.argtypes = [ci, ci]
     L.acb_lstm_state_bytes.restype = i64
@@ -75,7 +77,8 @@ def lib():
     for name in ('acb_weight_norm_fold', 'acb_conv1d', 'acb_convtr1d', 'acb_lstm_recurrent', 'acb_rvq_encode',
                  'acb_rvq_decode', 'acb_lm_create', 'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps',
                  'acb_lm_step_logits', 'acb_lm_launches_per_step', 'acb_lm_rows_pad', 'acb_sample',
-                 'acb_device_sm_count', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_debug_chain_latency'):
+                 'acb_device_sm_count', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_debug_chain_latency',
+                 'acb_conv1d_t6', 'acb_conv1d_t6_tile'):
         getattr(L, name).restype = ci
     _lib = L
     return L
@@ -85,7 +88,7 @@ def lib():
 EXPORTS = ['acb_version', 'acb_last_error', 'acb_device_sm_count', 'acb_weight_norm_fold', 'acb_conv1d', 'acb_convtr1d',
            'acb_lstm_recurrent', 'acb_lstm_state_bytes', 'acb_rvq_encode', 'acb_rvq_decode', 'acb_lm_create',
            'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps', 'acb_lm_step_logits', 'acb_lm_rows_pad',
-           'acb_lm_launches_per_step', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_sample', 'acb_debug_chain_latency']
+           'acb_lm_launches_per_step', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_sample', 'acb_debug_chain_latency', 'acb_conv1d_t6', 'acb_conv1d_t6_tile']
 
 
 def check(rc: int, what: str = ''):

@@ -542,6 +542,284 @@ static int launch_conv1d_t5(const ConvParams& p, int batch, cudaStream_t s) {
     return launch_t5_one<2, 4>(q, xsp, batch, s);
 }
 
+// ------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (round-2 candidate; written without GPU time left in round 1 -> NOT validated on hardware, not used by
+// EncodecModel; reachable only through acb_conv1d_t6 and a GPU test that is skipped unless ACB_TEST_EXPERIMENTAL=1).
+//
+// conv1d_t6: implicit-GEMM convolution on tcgen05 WITHOUT an im2col tile, warp-specialised and double-buffered, with
+// the TMEM accumulator flushed into fp32 registers once per 8-channel group.  It answers the two measured problems of
+// conv1d_t5_kernel (profiles/r1_ncu_t5v2_raw.csv):
+//   (1) t5 is BUILD-bound, not MMA-bound: per 32 reduction rows it writes a 128 x 32 im2col tile (every input sample
+//       is split and stored once per tap).  Here the reduction index of one MMA is 8 consecutive INPUT CHANNELS at a
+//       fixed tap, and the staged input slab is laid out [4-channel chunk][stride phase][time][4 channels], i.e. with
+//       SBO = 128 B the 128 time rows of the A operand are linear at 16 B pitch: a tap is just a different START ADDRESS
+//       of the shared-memory descriptor (phase plane (k*D) % S, row offset (k*D) / S).  Each input sample is split and
+//       stored once per 8-channel group instead of once per tap (7-16x less build work).
+//   (2) t5's error is the tensor core's truncating fp32 accumulate over up to 3 072 chained MMAs.  Here the chain is
+//       3*K MMAs (one 8-channel group); the epilogue warps tcgen05.ld that partial sum and add it to register
+//       accumulators with round-to-nearest fp32 adds while the MMA warp fills the other TMEM accumulator.
+// Roles (320 threads): warps 0-3 stage the input slab (ELU, reflect / zero padding, hi/lo tf32 split), warp 4 issues the
+// MMAs, warps 5-8 flush / own the output tile (TMEM lane quarter = warp % 4), warp 9 streams the pre-split, pre-laid-out
+// weight tiles with TMA bulk copies.  Pipelines: slab x2 (a_full / a_empty), weight stage x2 (b_full / b_empty),
+// TMEM accumulator x2 (acc_full / acc_empty); tcgen05.commit releases slab, weight stage and accumulator.
+// Weights are packed by the host as w6[co_tile][cg][k][term(hi,lo)][c(2)][n(N)][4 channels]  (fp32 bits, tf32-exact).
+// ------------------------------------------------------------------------------------------------
+constexpr int T6_M = 128, T6_THREADS = 320, T6_MAXV = 20;
+
+struct T6Params {
+    const float* x; const float* w6; const float* bias; const float* res; float* y;
+    int c_in, c_out, t_in, t_virt, t_out, K, S, D, pad_left, reflect, elu;
+    int span, PL, n_cg, TB;   // slab length, rows per phase plane, 8-channel groups, taps per weight stage
+};
+
+__device__ __forceinline__ void t6_mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32_(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void t6_mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32_(b)) : "memory");
+}
+__device__ __forceinline__ void t6_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32_(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void t6_mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t ok = 0;
+    do {
+        asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n selp.u32 %0, 1, 0, q;\n}"
+                     : "=r"(ok) : "r"(smem_u32_(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void t6_commit(uint64_t* b) {   // arrives on b once every MMA issued so far by this thread is done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32_(b)) : "memory");
+}
+__device__ __forceinline__ void t6_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32_(dst)), "l"(src), "r"(bytes), "r"(smem_u32_(bar)) : "memory");
+}
+
+// shared-memory layout (bytes), shared by kernel and launcher
+struct T6Smem { int slab_term, slab_stage, b_tap, b_stage, slab, btile, bars, total; };
+__host__ __device__ inline T6Smem t6_smem(int N, int S, int PL, int TB) {
+    T6Smem L;
+    L.slab_term = 2 * S * PL * 16;          // [c(2)][phase][row][4 floats]
+    L.slab_stage = 2 * L.slab_term;         // hi, lo
+    L.b_tap = 2 * 2 * N * 16;               // [term][c(2)][n][4 floats]
+    L.b_stage = TB * L.b_tap;
+    L.slab = 0;
+    L.btile = 2 * L.slab_stage;
+    L.bars = L.btile + 2 * L.b_stage;
+    L.total = L.bars + 12 * 8 + 16;
+    return L;
+}
+
+template <int N>
+__global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
+    extern __shared__ __align__(128) unsigned char t6sm[];
+    const T6Smem L = t6_smem(N, p.S, p.PL, p.TB);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(t6sm + L.bars);
+    uint64_t* a_full = bars;          // [2] slab staged            (1 arrival: elected producer)
+    uint64_t* a_empty = bars + 2;     // [2] slab consumed          (tcgen05.commit)
+    uint64_t* b_full = bars + 4;      // [2] weight stage landed    (1 arrival + TMA bytes)
+    uint64_t* b_empty = bars + 6;     // [2] weight stage consumed  (tcgen05.commit)
+    uint64_t* acc_full = bars + 8;    // [2] partial sum complete   (tcgen05.commit)
+    uint64_t* acc_empty = bars + 10;  // [2] partial sum flushed    (4 arrivals: one per epilogue warp)
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * T6_M, co0 = blockIdx.y * N, b = blockIdx.z;
+    const int nstage_b = (p.K + p.TB - 1) / p.TB;   // weight stages per channel group
+
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32_(tslot)), "n"(2 * N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            t6_mbar_init(a_full + i, 1); t6_mbar_init(a_empty + i, 1);
+            t6_mbar_init(b_full + i, 1); t6_mbar_init(b_empty + i, 1);
+            t6_mbar_init(acc_full + i, 1); t6_mbar_init(acc_empty + i, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tslot;
+
+    if (warp < 4) {
+        // ================= producers: stage the 8-channel slab of every channel group =================
+        // chunk-invariant maps: this thread's (time j, 4-channel chunk c) vectors -> source index / destination
+        const int nvec = 2 * p.span;
+        const int g0 = t0 * p.S - p.pad_left;
+        int src[T6_MAXV], dst[T6_MAXV];   // src: input index or -1 (padding) ; dst: byte offset inside one term's slab or -1
+#pragma unroll
+        for (int i = 0; i < T6_MAXV; ++i) {
+            const int e = tid + 128 * i;
+            src[i] = -1; dst[i] = -1;
+            if (e < nvec) {
+                const int c = e / p.span, j = e - c * p.span;
+                int g = g0 + j;
+                if (p.reflect) {
+                    if (g < 0) g = -g;
+                    if (g >= p.t_virt) g = 2 * (p.t_virt - 1) - g;
+                }
+                dst[i] = (((c * p.S + (j % p.S)) * p.PL + j / p.S) * 16) | (c << 30);
+                if (g >= 0 && g < p.t_in) src[i] = g;
+            }
+        }
+        const float* xb = p.x + (size_t)b * p.c_in * p.t_in;
+        for (int cg = 0; cg < p.n_cg; ++cg) {
+            const int st = cg & 1;
+            t6_mbar_wait(a_empty + st, ((cg >> 1) & 1) ^ 1);   // first use of each buffer passes at once
+            unsigned char* hi = t6sm + L.slab + st * L.slab_stage;
+            unsigned char* lo = hi + L.slab_term;
+#pragma unroll
+            for (int i = 0; i < T6_MAXV; ++i) {
+                if (dst[i] < 0) continue;
+                const int c = (dst[i] >> 30) & 1, off = dst[i] & 0x3FFFFFFF;
+                const float* xc = xb + (size_t)(cg * 8 + c * 4) * p.t_in;
+                float v[4], h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    v[q] = src[i] >= 0 ? __ldg(xc + (size_t)q * p.t_in + src[i]) : 0.f;
+                    if (p.elu) v[q] = acb_elu(v[q]);
+                    h[q] = __uint_as_float(to_tf32(v[q]));
+                    l[q] = __uint_as_float(to_tf32(v[q] - h[q]));
+                }
+                *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+            asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four producer warps
+            if (tid == 0) t6_mbar_arrive(a_full + st);
+        }
+    } else if (warp == 9) {
+        // ================= weight loader: one TMA bulk copy per weight stage =================
+        if (lane == 0) {
+            const unsigned char* wbase = reinterpret_cast<const unsigned char*>(p.w6) +
+                                         (size_t)blockIdx.y * p.n_cg * p.K * L.b_tap;
+            int it = 0;
+            for (int cg = 0; cg < p.n_cg; ++cg)
+                for (int sb = 0; sb < nstage_b; ++sb, ++it) {
+                    const int bs = it & 1, k0 = sb * p.TB, ntap = min(p.TB, p.K - k0);
+                    t6_mbar_wait(b_empty + bs, ((it >> 1) & 1) ^ 1);
+                    const uint32_t bytes = (uint32_t)ntap * (uint32_t)L.b_tap;
+                    t6_mbar_expect_tx(b_full + bs, bytes);
+                    t6_bulk_g2s(t6sm + L.btile + bs * L.b_stage, wbase + ((size_t)cg * p.K + k0) * L.b_tap, bytes, b_full + bs);
+                }
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T6_M >> 4) << 24);
+            const uint32_t lbo_a = (uint32_t)(p.S * p.PL * 16), lbo_b = (uint32_t)N * 16u;
+            const uint32_t slab_s = smem_u32_(t6sm + L.slab), btile_s = smem_u32_(t6sm + L.btile);
+            int it = 0;
+            for (int cg = 0; cg < p.n_cg; ++cg) {
+                const int st = cg & 1, acc = cg & 1;
+                t6_mbar_wait(acc_empty + acc, ((cg >> 1) & 1) ^ 1);
+                t6_mbar_wait(a_full + st, (cg >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem + (uint32_t)(acc * N);
+                uint32_t accumulate = 0;
+                for (int sb = 0; sb < nstage_b; ++sb, ++it) {
+                    const int bs = it & 1, k0 = sb * p.TB, ntap = min(p.TB, p.K - k0);
+                    t6_mbar_wait(b_full + bs, (it >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int kk = 0; kk < ntap; ++kk) {
+                        const int kd = (k0 + kk) * p.D;
+                        const uint32_t a_off = (uint32_t)(((kd % p.S) * p.PL + kd / p.S) * 16);
+                        const uint64_t a_hi = t5_desc(slab_s + st * L.slab_stage + a_off, lbo_a);
+                        const uint64_t a_lo = t5_desc(slab_s + st * L.slab_stage + L.slab_term + a_off, lbo_a);
+                        const uint32_t bt = btile_s + bs * L.b_stage + kk * L.b_tap;
+                        const uint64_t b_hi = t5_desc(bt, lbo_b), b_lo = t5_desc(bt + 2 * N * 16, lbo_b);
+                        t5_mma(d_tmem, a_lo, b_hi, idesc, accumulate);   // small cross terms first
+                        t5_mma(d_tmem, a_hi, b_lo, idesc, 1u);
+                        t5_mma(d_tmem, a_hi, b_hi, idesc, 1u);
+                        accumulate = 1u;
+                    }
+                    t6_commit(b_empty + bs);          // the weight stage may be overwritten once these MMAs are done
+                }
+                t6_commit(a_empty + st);              // ... and so may the slab
+                t6_commit(acc_full + acc);            // ... and the partial sum is complete
+            }
+        }
+    } else {
+        // ================= epilogue warps 5-8: flush partial sums, then bias / residual / store =================
+        const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are the ones this warp may read
+        const int t = t0 + quarter * 32 + lane;
+        float accr[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) accr[j] = 0.f;
+        for (int cg = 0; cg < p.n_cg; ++cg) {
+            const int acc = cg & 1;
+            t6_mbar_wait(acc_full + acc, (cg >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N + c0);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) accr[c0 + j] += __uint_as_float(v[j]);   // round-to-nearest fp32 adds
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) t6_mbar_arrive(acc_empty + acc);
+        }
+        if (t < p.t_out) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const int co = co0 + j;
+                if (co < p.c_out) {
+                    const size_t o = ((size_t)b * p.c_out + co) * p.t_out + t;
+                    float yv = accr[j] + (p.bias ? p.bias[co] : 0.f);
+                    if (p.res) yv += p.res[o];
+                    p.y[o] = yv;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * N) : "memory");
+}
+
+template <int N>
+static int launch_t6_one(const T6Params& q, int batch, cudaStream_t s) {
+    const T6Smem L = t6_smem(N, q.S, q.PL, q.TB);
+    ACB_REQUIRE(L.total <= 220 * 1024, "acb_conv1d_t6: tile needs %d B of shared memory", L.total);
+    ACB_CHECK_CUDA(cudaFuncSetAttribute(conv1d_t6_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    dim3 grid(acb_ceil_div(q.t_out, T6_M), q.c_out / N, batch);
+    conv1d_t6_kernel<N><<<grid, T6_THREADS, (size_t)L.total, s>>>(q);
+    ACB_LAUNCH_CHECK();
+    return ACB_OK;
+}
+
+extern "C" int acb_conv1d_t6_tile(int c_out) { return c_out % 128 == 0 ? 128 : (c_out % 64 == 0 ? 64 : 0); }
+
+extern "C" int acb_conv1d_t6(const float* x, const float* w6, const float* bias, const float* residual, float* y, int batch,
+                             int c_in, int c_out, int t_in, int t_virtual, int t_out, int kernel, int stride, int dilation,
+                             int pad_left, int reflect, int elu_in, void* stream) {
+    ACB_REQUIRE(x && w6 && y, "acb_conv1d_t6: null pointer");
+    ACB_REQUIRE(batch > 0 && batch <= 65535 && c_in > 0 && c_out > 0 && t_in > 0 && t_out > 0, "acb_conv1d_t6: bad shape");
+    ACB_REQUIRE(kernel >= 1 && kernel <= 64 && stride >= 1 && dilation >= 1 && pad_left >= 0 && t_virtual >= t_in, "acb_conv1d_t6: bad taps");
+    ACB_REQUIRE(c_in % 8 == 0, "acb_conv1d_t6: c_in %d is not a multiple of 8 (one MMA reduces over 8 channels)", c_in);
+    const int N = acb_conv1d_t6_tile(c_out);
+    ACB_REQUIRE(N != 0, "acb_conv1d_t6: c_out %d is not a multiple of 64", c_out);
+    T6Params q{x, w6, bias, residual, y, c_in, c_out, t_in, t_virtual, t_out, kernel, stride, dilation, pad_left, reflect, elu_in,
+               0, 0, c_in / 8, 0};
+    q.span = (T6_M - 1) * stride + (kernel - 1) * dilation + 1;
+    q.PL = acb_ceil_div(q.span, stride);
+    q.TB = kernel < 4 ? kernel : 4;
+    ACB_REQUIRE(2 * q.span <= 128 * T6_MAXV, "acb_conv1d_t6: slab too long (%d samples per channel)", q.span);
+    cudaStream_t s = (cudaStream_t)stream;
+    return N == 128 ? launch_t6_one<128>(q, batch, s) : launch_t6_one<64>(q, batch, s);
+}
+
 // Few output channels (the decoder's last conv, Cout = audio channels): a thread owns 4 consecutive output steps of
 // every output channel and slides a register window over the taps, so the kernel is a pure stream over x.
 constexpr int SC_MAXCO = 4, SC_TILE = 1024;

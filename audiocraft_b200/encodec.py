@@ -116,6 +116,24 @@ def convtr_geometry(length: int, kernel: int, stride: int, causal: bool, trim_ri
     return left, t_full - left - right
 
 
+def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest tf32-representable fp32 (10-bit mantissa), ties away from zero: what `cvt.rna.tf32.f32` returns."""
+    bits = x.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & -8192).view(torch.float32)
+
+
+def pack_conv_t6(w: torch.Tensor, tile: int) -> torch.Tensor:
+    """Weights [c_out][c_in][K] (weight-norm folded) -> the operand layout of the experimental `acb_conv1d_t6`:
+    two tf32 terms (hi, lo = tf32(w - hi)) as [c_out/tile][c_in/8][K][term][2][tile][4]: per (tile, 8-channel group, tap)
+    a K-major UMMA B operand (rows = output channels at 16 B pitch, two 4-channel chunks tile*16 B apart)."""
+    co, ci, K = w.shape
+    assert co % tile == 0 and ci % 8 == 0, (w.shape, tile)
+    hi = tf32_round(w.float())
+    lo = tf32_round(w.float() - hi)
+    t = torch.stack([hi, lo]).view(2, co // tile, tile, ci // 8, 2, 4, K)   # term, tile, n, cg, c, j, k
+    return t.permute(1, 3, 6, 0, 4, 2, 5).contiguous()                      # tile, cg, k, term, c, n, j
+
+
 class EncodecModel(CompressionModel):
     """EnCodec (SEANet + RVQ) on B200 behind the reference's ``EncodecModel`` API."""
 

@@ -74,6 +74,17 @@ int acb_conv1d(const float* x, const float* w_packed, const float* bias, const f
 int acb_convtr1d(const float* x, const float* w_packed, const float* w_gemm, const float* bias, float* y,
                  int batch, int c_in, int c_out, int t_in, int t_out, int kernel, int stride, int trim_left,
                  int elu_in, int precision, void* stream);
+
+/* EXPERIMENTAL (round-2 candidate, not validated on hardware yet, not used by EncodecModel): the same convolution as
+ * acb_conv1d (StreamableConv1d.forward, modules/conv.py:185-201, + fused ELU / residual) as an implicit GEMM on tcgen05
+ * without an im2col tile, the TMEM accumulator flushed into fp32 registers once per 8 input channels (csrc/encodec.cu,
+ * conv1d_t6_kernel).  c_in % 8 == 0 and c_out % 64 == 0.  w6 = weights split into two tf32 terms and laid out as
+ * [c_out / N][c_in / 8][kernel][term hi,lo][2][N][4] with N = acb_conv1d_t6_tile(c_out)
+ * (audiocraft_b200.encodec.pack_conv_t6 builds it). */
+int acb_conv1d_t6(const float* x, const float* w6, const float* bias, const float* residual, float* y, int batch,
+                  int c_in, int c_out, int t_in, int t_virtual, int t_out, int kernel, int stride, int dilation,
+                  int pad_left, int reflect, int elu_in, void* stream);
+int acb_conv1d_t6_tile(int c_out);   /* output-channel tile (128, 64, or 0 = shape not supported) */
 /* w_gemm (optional, needed for precision ACB_CONV_TF32X3): the same weights packed as the GEMM operand
  * [2*Cin][Cout*stride], row r = ci*2 + k (k = 0 multiplies x[ti-1], k = 1 multiplies x[ti]), column n' = co*stride + ph,
  * value w[ci][ph + (1-k)*stride][co]: the transposed conv then runs on the tcgen05 kernel as one GEMM whose accumulator
