@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libaudiocraft_b200.so')
 
 CONV_FP32, CONV_TF32X3, CONV_TF32X3_MMASYNC = 0, 1, 2
+CONV_T6_FLUSH = 3   # host-side selector only: layers that qualify go through the EXPERIMENTAL acb_conv1d_t6, the rest fp32
 ACB_LM_MAX_SPLIT = 8
 ACB_LM_PLAN_BYTES = 2 << 20
 

@@ -143,8 +143,11 @@ class EncodecModel(CompressionModel):
         defaults to fp32 so that RVQ indices equal the fp32 reference's; the decoder's output is a waveform checked to a
         tolerance (1e-4) and defaults to the faster 3xTF32 convolutions."""
         self.device = _lib.require_cuda(device)
-        prec = {'fp32': _lib.CONV_FP32, 'tf32x3': _lib.CONV_TF32X3, 'tf32x3_mmasync': _lib.CONV_TF32X3_MMASYNC}
+        # ('tf32x3_flush' is EXPERIMENTAL and not validated on hardware yet: implicit-GEMM tcgen05 convs with fp32 flushes)
+        prec = {'fp32': _lib.CONV_FP32, 'tf32x3': _lib.CONV_TF32X3, 'tf32x3_mmasync': _lib.CONV_TF32X3_MMASYNC,
+                'tf32x3_flush': _lib.CONV_T6_FLUSH}
         self._enc_prec, self._dec_prec = prec[encoder_precision], prec[decoder_precision]
+        self._want_t6 = _lib.CONV_T6_FLUSH in (self._enc_prec, self._dec_prec)
         # the LSTM input projections (one 1x1 conv per layer) always run on the tensor cores: measured 3.9e-6 vs 3.6e-6 latent
         # error for the otherwise-fp32 encoder (the tensor-core error of the conv stack comes from its long reductions)
         self._lstm_prec = _lib.CONV_TF32X3
@@ -192,6 +195,9 @@ class EncodecModel(CompressionModel):
             w = self._fold(sd, p)                                       # [Cout][Cin][K]
             out['w'] = w.permute(1, 2, 0).reshape(-1, w.shape[0]).contiguous()   # [Cin*K][Cout]
             out['b'] = sd[p + 'bias'].to(self.device, torch.float32).contiguous()
+            tile = int(self._lib.acb_conv1d_t6_tile(w.shape[0])) if self._want_t6 else 0
+            if tile and w.shape[1] % 8 == 0:
+                out['w6'] = pack_conv_t6(w, tile)
         elif layer['kind'] == 'convtr':
             w = self._fold(sd, p)                                       # [Cin][Cout][K]
             out['w'] = w.permute(0, 2, 1).contiguous()                  # [Cin][K][Cout]
@@ -220,6 +226,15 @@ class EncodecModel(CompressionModel):
         cout = L['cout'] if cout is None else cout
         left, t_virt, t_out = conv_geometry(T, k, stride, dilation, self.causal, bool(self.reflect))
         y = torch.empty((B, cout, t_out), device=x.device, dtype=torch.float32)
+        if prec == _lib.CONV_T6_FLUSH:
+            if w is None and 'w6' in L and cout == L['cout']:
+                _lib.check(self._lib.acb_conv1d_t6(_lib.ptr(x), _lib.ptr(L['w6']), _lib.ptr(L['b'] if b is None else b),
+                                                   _lib.ptr(res), _lib.ptr(y), B, cin, cout, T, t_virt, t_out, k, stride,
+                                                   dilation, left, self.reflect, int(L['elu'] if elu is None else elu),
+                                                   _lib.stream()), 'conv1d_t6')
+                self.launches += 1
+                return y
+            prec = _lib.CONV_FP32          # layers the implicit-GEMM kernel does not take keep fp32 accuracy on the FMA path
         _lib.check(self._lib.acb_conv1d(_lib.ptr(x), _lib.ptr(L['w'] if w is None else w),
                                         _lib.ptr(L['b'] if b is None else b), _lib.ptr(res), _lib.ptr(y),
                                         B, cin, cout, T, t_virt, t_out, k, stride, dilation, left, self.reflect,
@@ -231,6 +246,8 @@ class EncodecModel(CompressionModel):
         B, cin, T = x.shape
         trim_left, t_out = convtr_geometry(T, L['k'], L['stride'], self.causal, self.cfg['trim_right_ratio'])
         y = torch.empty((B, L['cout'], t_out), device=x.device, dtype=torch.float32)
+        if prec == _lib.CONV_T6_FLUSH:
+            prec = _lib.CONV_TF32X3        # transposed convs have no implicit-GEMM variant yet
         _lib.check(self._lib.acb_convtr1d(_lib.ptr(x), _lib.ptr(L['w']), _lib.ptr(L['w_gemm']), _lib.ptr(L['b']),
                                           _lib.ptr(y), B, cin, L['cout'], T, t_out, L['k'], L['stride'], trim_left,
                                           int(L['elu']), prec, _lib.stream()), 'convtr1d')

@@ -295,6 +295,24 @@ def test_tensor_core_encoder_mode(name):
     assert (codes.cpu() == g['codes']).float().mean() > 0.98
 
 
+@pytest.mark.skipif(os.environ.get('ACB_TEST_EXPERIMENTAL') != '1', reason='conv1d_t6 not validated on hardware yet (round 2)')
+@pytest.mark.parametrize('name', ['encodec_32k', 'encodec_24k'])
+def test_experimental_flush_encoder_mode(name):
+    """encoder_precision='tf32x3_flush': the implicit-GEMM tcgen05 convs with per-8-channel fp32 flushes are meant to make
+    the tensor-core encoder as accurate as the fp32 FMA one (latents atol 2e-5, codes under the exact-encoder rule)."""
+    from audiocraft_b200.encodec import EncodecModel
+    g = torch.load(os.path.join(H.GOLDEN_DIR, f'{name}.pt'), weights_only=False)
+    cfg = synth.ENCODEC_CONFIGS[name]
+    sd = synth.synth_encodec_state_dict(cfg, seed=g['wseed'])
+    x = H.audio_input(cfg, g['batch'], g['length'], g['xseed'])
+    m = EncodecModel(sd, cfg, encoder_precision='tf32x3_flush')
+    lat = m.encode_latent(x.cuda()).cpu()
+    print(f'{name} flush-mode encoder latent max err {(lat - g["latent"]).abs().max():.2e}')
+    torch.testing.assert_close(lat, g['latent'], rtol=0, atol=2e-5)
+    codes, _ = m.encode(x)
+    assert (codes.cpu() == g['codes']).float().mean() > 0.999
+
+
 @pytest.mark.parametrize('shortcut', [False, True])
 def test_hf_encodec_checkpoint_on_kernels(shortcut):
     """an HF-format EnCodec checkpoint (random init here) converted and run on the kernels vs
