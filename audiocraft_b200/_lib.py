@@ -75,21 +75,23 @@ def lib():
     L.acb_lm_debug_gemms.argtypes = [vp, vp, C.POINTER(ci)]
     L.acb_sample.argtypes = [vp, vp, vp, ci, ci, ci, ci, C.POINTER(LMSampling), C.c_uint64, vp]
     L.acb_debug_chain_latency.argtypes = [ci, ci, ci, ci, ci, ci, C.POINTER(C.c_float), vp]
+    L.acb_debug_grid_barrier.argtypes = [ci, ci, ci, ci, ci, ci, C.POINTER(C.c_float)]
     for name in ('acb_weight_norm_fold', 'acb_conv1d', 'acb_convtr1d', 'acb_lstm_recurrent', 'acb_rvq_encode',
                  'acb_rvq_decode', 'acb_lm_create', 'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps',
                  'acb_lm_step_logits', 'acb_lm_launches_per_step', 'acb_lm_rows_pad', 'acb_sample',
                  'acb_device_sm_count', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_debug_chain_latency',
-                 'acb_conv1d_t6', 'acb_conv1d_t6_tile'):
+                 'acb_conv1d_t6', 'acb_conv1d_t6_tile', 'acb_debug_grid_barrier'):
         getattr(L, name).restype = ci
     _lib = L
     return L
 
 
-# every symbol include/audiocraft_b200.h declares (checked by tests/test_abi.py against the header text)
+# every symbol include/audiocraft_b200.h declares (checked by tests/test_host.py against the header text)
 EXPORTS = ['acb_version', 'acb_last_error', 'acb_device_sm_count', 'acb_weight_norm_fold', 'acb_conv1d', 'acb_convtr1d',
            'acb_lstm_recurrent', 'acb_lstm_state_bytes', 'acb_rvq_encode', 'acb_rvq_decode', 'acb_lm_create',
            'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps', 'acb_lm_step_logits', 'acb_lm_rows_pad',
-           'acb_lm_launches_per_step', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_sample', 'acb_debug_chain_latency', 'acb_conv1d_t6', 'acb_conv1d_t6_tile']
+           'acb_lm_launches_per_step', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_sample', 'acb_debug_chain_latency', 'acb_conv1d_t6', 'acb_conv1d_t6_tile',
+           'acb_debug_grid_barrier']
 
 
 def check(rc: int, what: str = ''):

@@ -280,10 +280,12 @@ class LMModel:
 
     @torch.no_grad()
     def teacher_forced_logits(self, sequence: torch.Tensor, cross: tp.Optional[torch.Tensor], cfg_coef: float,
-                              n_steps: tp.Optional[int] = None) -> torch.Tensor:
+                              n_steps: tp.Optional[int] = None, keep: tp.Optional[tp.Sequence[int]] = None,
+                              raw: bool = False):
         """Feed a fully known delay-pattern sequence [B,K,S] token by token and return the (CFG-mixed when cross has
         2B rows) next-token logits [n_steps,B,K,card] -- LMModel.forward in streaming mode (lm.py:221-268), the
-        quantity the parity tests compare against the oracle."""
+        quantity the parity tests compare against the oracle.  ``keep``: only these step indices are returned (in that
+        order; every step still runs).  ``raw``: also return the un-mixed per-row logits [n,rows,K,card] ([cond; null])."""
         with torch.cuda.device(self.device):
             sequence = sequence.to(self.device, torch.long)
             B, K, S = sequence.shape
@@ -300,7 +302,14 @@ class LMModel:
                                               _lib.stream()), 'lm_begin')
             self.launches_per_step = self._lib.acb_lm_launches_per_step(self._handle)
             n = S - 1 if n_steps is None else n_steps
-            out = torch.empty((n, B, K, self.card), device=self.device, dtype=torch.float32)
-            for i in range(n):
-                _lib.check(self._lib.acb_lm_step_logits(self._handle, out[i].data_ptr(), _lib.stream()), 'lm_step_logits')
-            return out
+            slot = {i: j for j, i in enumerate(range(n) if keep is None else keep)}
+            out = torch.empty((len(slot), B, K, self.card), device=self.device, dtype=torch.float32)
+            raw_out = torch.empty((len(slot), rows, K, self.card), device=self.device, dtype=torch.float32) if raw else None
+            last = max(slot) if slot else -1
+            for i in range(min(n, last + 1)):
+                j = slot.get(i)
+                _lib.check(self._lib.acb_lm_step_logits(self._handle, out[j].data_ptr() if j is not None else None,
+                                                        _lib.stream()), 'lm_step_logits')
+                if raw and j is not None:
+                    raw_out[j].copy_(bufs['logits'][:rows].view(rows, K, self.card))
+            return (out, raw_out) if raw else out

@@ -10,9 +10,13 @@ inputs (condition tensors) resident in HBM.  `e2e` = the same through the public
 with host inputs (text-encoder states pinned on the host, copied inside the timed region) and the waveform read back.
 Weights are seeded random (no checkpoints offline), inputs synthetic.
 
-`--impl reference` times the reference's own CPU implementation of the path: /root/reference does not exist on the GPU
-box, so it runs the oracle port (oracle/lm_oracle.py + oracle/encodec_oracle.py, fp32, all host threads) on a bounded
-sample of the same workload.
+`--impl reference` times the reference's OWN code on the box's host cores: the unmodified package installed under
+baseline/_ref (baseline/install_ref.sh; it ships with the snapshot), driven through oracle/ref_import.py's third-party
+stubs by baseline/reference_arm.py.  One "step" of that arm is one bounded sample of the same workload (a few decode
+steps of LMModel.generate's loop at KV length 1 and at the final KV length + the EnCodec decode of 1 s of tokens),
+integrated to the full pass; `ms_per_step` is the sample's wall time.  The b200 line carries the same measurement as
+`cpu_baseline` and, as `reference_gpu`, the reference's CUDA path (fp16 autocast, SDPA, eager) timed over full passes on
+the same GPU -- the competitor north_star names.
 """
 import argparse
 import json
@@ -259,8 +263,24 @@ def run_b200(args):
         del cm_fast
 
     cpu_baseline = None
+    reference_gpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_ref_gpu:
+        # the reference's own CUDA path on this box (both models stay resident: ~15 GB of 180)
+        from baseline import reference_arm as RA
+        if RA.available():
+            try:
+                reference_gpu = RA.gpu_reference(args.scale, B, dur, passes=2, encodec_items=0 if args.no_encodec else 32)
+            except Exception as ex:   # the arm must never take the product line down
+                reference_gpu = dict(unavailable=f'{type(ex).__name__}: {ex}'[:300])
+            torch.cuda.empty_cache()
+        else:
+            reference_gpu = dict(unavailable='baseline/_ref is not installed')
     if rank == 0 and args.gpus == 1 and not args.no_cpu:
-        cpu_baseline = cpu_reference(args, sample_steps=args.cpu_steps)
+        cpu_baseline = cpu_reference(args)
+        if secondary is not None:
+            from baseline import reference_arm as RA
+            if RA.available():
+                secondary['cpu_baseline'] = RA.cpu_encodec_baseline(1, 10.0)
 
     if rank == 0:
         line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -274,63 +294,47 @@ def run_b200(args):
                     clocks=clocks,
                     e2e=dict(value=round(e2e_value, 2), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes),
                     gpu_launches=(lm.launches_per_step * (S - 1) + dec_launches) * args.steps,
-                    roofline=roofline, cpu_baseline=cpu_baseline, secondary=secondary)
+                    roofline=roofline, cpu_baseline=cpu_baseline, reference_gpu=reference_gpu, secondary=secondary)
         emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
 
 
-def cpu_reference(args, sample_steps):
-    """The oracle port of the reference's CPU path on the host cores: the first `sample_steps` decode steps of the same
-    workload (rows = 2B, fp32, all threads) + EnCodec-32k decode of 1 s of tokens, scaled to audio-s/s."""
-    from oracle import lm_oracle as LO
-    from audiocraft_b200 import synth
-    avail = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-    # rows=16 GEMVs do not scale past a few dozen threads (and oversubscribed OpenMP teams collapse): cap at 32
-    cores = max(1, min(avail, 32))
-    torch.set_num_threads(cores)
-    cfg = synth.lm_config({'small': 'musicgen_small', 'medium': 'musicgen_medium', 'large': 'musicgen_large'}[args.scale])
-    gdev = 'cuda' if torch.cuda.is_available() else 'cpu'
-    sd = synth.synth_lm_state_dict(cfg, 0, device=gdev, dtype=torch.float16 if gdev == 'cuda' else torch.float32)
-    sd = {k: v.float().cpu() for k, v in sd.items()}
-    B = args.batch
-    o = LO.LMOracle(sd, cfg)
-    del sd
-    cross = torch.randn(2 * B, 16, cfg['dim']) * 0.1
-    cross[B:] = 0
-    seq = torch.full((B, cfg['n_q'], 1), cfg['card'], dtype=torch.long)
-    o.reset()
-    g = torch.Generator().manual_seed(0)
-    o.next_token(seq, cross, True, 1.0, 250, 0.0, 3.0, g, None)  # warm-up step (also fills 1 KV entry)
-    t0 = time.perf_counter()
-    done = 0
-    while done < sample_steps and (done < 2 or time.perf_counter() - t0 < 20.0):   # bounded: ~20 s of CPU work
-        seq = o.next_token(seq, cross, True, 1.0, 250, 0.0, 3.0, g, None)
-        done += 1
-    dt = time.perf_counter() - t0
-    sample_steps = done
-    per_step = dt / sample_steps
-    frame_rate = 50.0
-    value = B / frame_rate / per_step  # audio seconds per wall second (EnCodec decode excluded: <1% of the CPU time)
-    return dict(value=round(value, 4), unit=UNIT, cores=cores, kind='port',
-                sample=f'{sample_steps} decode steps of the batch={B} (rows={2 * B}) {args.scale} generation at KV length<= '
-                       f'{sample_steps + 1}, fp32 oracle port, {per_step * 1e3:.0f} ms/step; short-context steps are the '
-                       f'cheapest ones, so this favours the CPU')
+def cpu_reference(args, n_samples=2):
+    """cpu_baseline: the reference's own modules (baseline/_ref) on the host cores, bounded samples (reference_arm.py)."""
+    from baseline import reference_arm as RA
+    if not RA.available():
+        return dict(value=None, unit=UNIT, cores=0, kind='unavailable', sample='baseline/_ref is not installed (baseline/install_ref.sh)')
+    return RA.cpu_baseline(args.scale, args.batch, args.duration, n_samples=n_samples, n_steps=args.cpu_steps)
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    t0 = time.perf_counter()
-    cb = cpu_reference(args, sample_steps=max(2, args.cpu_steps))
+    from baseline import reference_arm as RA
+    if not RA.available():
+        emit(dict(impl='reference', unavailable='baseline/_ref is not installed (run baseline/install_ref.sh in the build container)'))
+        return
+    from oracle import ref_import as R
+    ref = RA.CpuReference(args.scale, args.batch, args.duration)
+    for _ in range(args.warmup):
+        ref.sample(n_steps=1, ctx=64)
+    smps = [ref.sample(n_steps=args.cpu_steps) for _ in range(args.steps)]
+    order = sorted(smps, key=lambda q: q['value'])
+    med = order[len(order) // 2]
+    cb = dict(value=round(med['value'], 4), unit=UNIT, cores=ref.threads, kind='reference' if R.kind() == '_ref' else 'reference-tree',
+              sample=ref.describe(med), spread=[round(q['value'], 4) for q in smps])
     line = dict(metric=METRIC, value=cb['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=round((time.perf_counter() - t0) * 1e3, 1), higher_is_better=True, scaling='weak',
+                ms_per_step=round(sum(q['wall_s'] for q in smps) / len(smps) * 1e3, 1), higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
                 config=dict(workload=f'MusicGen-{args.scale} text-conditioned {args.duration:g}s generation, batch={args.batch} '
-                                     f'(CFG rows={2 * args.batch}); bounded sample, see cpu_baseline.sample'),
-                cpu_baseline=cb, e2e=dict(value=cb['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                                     f'(CFG rows={2 * args.batch}), top_k=250, EnCodec-32k decode included; each step is a bounded '
+                                     f'sample integrated to the full pass (cpu_baseline.sample)',
+                            global_batch=args.batch, seq_len=int(args.duration * 50), parallelism='host cores (rank 0 only)'),
+                gpu_launches=0, cpu_baseline=cb,
+                e2e=dict(value=cb['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
 
 
@@ -364,8 +368,9 @@ if __name__ == '__main__':
     ap.add_argument('--scale', default='medium', choices=['small', 'medium', 'large'])
     ap.add_argument('--duration', type=float, default=30.0)
     ap.add_argument('--batch', type=int, default=8)
-    ap.add_argument('--cpu-steps', type=int, default=24)
+    ap.add_argument('--cpu-steps', type=int, default=4, help='decode steps per KV window of one CPU reference sample')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-ref-gpu', action='store_true', help='skip timing the reference CUDA path (reference_gpu block)')
     ap.add_argument('--no-encodec', action='store_true')
     a = ap.parse_args()
     if a.impl == 'reference':

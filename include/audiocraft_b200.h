@@ -227,6 +227,12 @@ int acb_lm_launches_per_step(const acb_lm_t* lm);
 int acb_debug_chain_latency(int n_kernels, int ctas, int threads, int smem, int pdl, int reps, float* us_per_kernel,
                             void* scratch);
 
+/* Measurement aid (no reference counterpart): microseconds per grid-wide barrier of a cooperative kernel of `ctas`
+ * co-resident CTAs x `threads` that does nothing but `n_barriers` barriers (`work` dependent FMAs in between).
+ * variant 0 = the barrier the persistent decode step uses (csrc/gridbar.cuh), 1 = relaxed polling, 2 = fence + atomicAdd +
+ * volatile spin. */
+int acb_debug_grid_barrier(int ctas, int threads, int n_barriers, int variant, int work, int reps, float* us_per_barrier);
+
 /* Stand-alone sampler (tail of _sample_next_token, lm.py:403-418; utils/utils.py:88-141) for unit tests:
  * logits [rows][n_q][card] fp32 ([cond; null] rows when rows == 2*batch), noise optional, tokens [batch][n_q]. */
 int acb_sample(const float* logits, const float* noise, int64_t* tokens, int batch, int rows, int n_q, int card,

@@ -1,9 +1,11 @@
-"""Import the real reference modules (read-only tree at /root/reference) on CPU.
+"""Import the real reference modules, unmodified, on CPU or CUDA.
 
-TEST INFRASTRUCTURE ONLY. Works only in the build container (the GPU box has no
-/root/reference). Used by tests/golden/make_golden.py to generate the committed
-golden vectors, and by the `not gpu` tests that cross-check oracle/ against the
-reference when the tree is present.
+TEST / BASELINE INFRASTRUCTURE ONLY (never imported by the audiocraft_b200 package).  The reference is looked up in
+this order: $AUDIOCRAFT_REFERENCE, /root/reference (build container only), <repo>/baseline/_ref -- the offline
+`pip install --no-deps --target baseline/_ref /root/reference` copy, git-ignored but shipped to the GPU box with the
+gpurun snapshot (recipe: baseline/install_ref.sh).  Used by tests/golden/make_golden.py to generate the committed
+golden vectors, by the tests that cross-check oracle/ and the CUDA path against the reference when it is present, and
+by bench.py's `--impl reference` arm and `reference_gpu` block (the reference's own modules timed on the box).
 
 Recipe: the reference's hot-path modules import and run on CPU
 once the missing third-party packages are stubbed. Nothing from the reference is
@@ -15,11 +17,27 @@ import types
 import importlib
 from unittest.mock import MagicMock
 
-REF_ROOT = os.environ.get("AUDIOCRAFT_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("AUDIOCRAFT_REFERENCE"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "audiocraft", "modules")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REF_ROOT, "audiocraft"))
+    return os.path.isdir(os.path.join(REF_ROOT, "audiocraft", "modules"))
+
+
+def kind() -> str:
+    """'tree' = the read-only source tree, '_ref' = the pip-installed copy under baseline/_ref."""
+    return "_ref" if os.path.abspath(REF_ROOT).endswith(os.path.join("baseline", "_ref")) else "tree"
 
 
 _done = False

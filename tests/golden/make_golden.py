@@ -21,47 +21,11 @@ warnings.filterwarnings('ignore')
 torch.set_grad_enabled(False)
 
 
-def build_ref_encodec(cfg, sd):
-    seanet, qt, enc = R.mod('modules.seanet'), R.mod('quantization'), R.mod('models.encodec')
-    kw = dict(channels=cfg['channels'], dimension=cfg['dimension'], n_filters=cfg['n_filters'],
-              n_residual_layers=cfg['n_residual_layers'], ratios=cfg['ratios'], norm=cfg['norm'],
-              kernel_size=cfg['kernel_size'], last_kernel_size=cfg['last_kernel_size'],
-              residual_kernel_size=cfg['residual_kernel_size'], dilation_base=cfg['dilation_base'],
-              causal=cfg['causal'], pad_mode=cfg['pad_mode'], compress=cfg['compress'], lstm=cfg['lstm'])
-    m = enc.EncodecModel(seanet.SEANetEncoder(**kw), seanet.SEANetDecoder(**kw, trim_right_ratio=cfg['trim_right_ratio']),
-                         qt.ResidualVectorQuantizer(dimension=cfg['dimension'], n_q=cfg['n_q'], bins=cfg['bins'],
-                                                    kmeans_init=False),
-                         frame_rate=cfg['sample_rate'] // synth.encodec_hop(cfg), sample_rate=cfg['sample_rate'],
-                         channels=cfg['channels'], causal=cfg['causal'], renormalize=cfg['renormalize'])
-    m.load_state_dict(sd, strict=True)
-    return m.eval()
+from oracle.ref_models import build_ref_encodec, build_ref_lm as _build_ref_lm  # noqa: E402
 
 
 def build_ref_lm(cfg, sd, table):
-    lmm, cond, pat = R.mod('models.lm'), R.mod('modules.conditioners'), R.mod('modules.codebooks_patterns')
-
-    class StubText(cond.TextConditioner):
-        """Stands in for T5Conditioner (no T5 weights offline): same contract, hidden states from a table."""
-        def __init__(self, dim, output_dim):
-            super().__init__(dim, output_dim)
-
-        def tokenize(self, x):
-            hs, ms = zip(*[table['__null__'] if xi is None else table[xi] for xi in x])
-            return {'hid': torch.stack(hs), 'mask': torch.stack(ms)}
-
-        def forward(self, inputs):
-            mask = inputs['mask']
-            return self.output_proj(inputs['hid']) * mask.unsqueeze(-1), mask
-
-    prov = cond.ConditioningProvider({'description': StubText(cfg['cond_dim'], cfg['dim'])})
-    fuser = cond.ConditionFuser({'cross': ['description'], 'sum': [], 'prepend': [], 'input_interpolate': []})
-    m = lmm.LMModel(pat.DelayedPatternProvider(cfg['n_q'], delays=cfg['delays']), prov, fuser, n_q=cfg['n_q'],
-                    card=cfg['card'], dim=cfg['dim'], num_heads=cfg['num_heads'], hidden_scale=cfg['hidden_scale'],
-                    norm='layer_norm', norm_first=True, bias_proj=False, cfg_coef=cfg['cfg_coef'],
-                    num_layers=cfg['num_layers'], bias_ff=False, bias_attn=False, causal=True, memory_efficient=True,
-                    cross_attention=True, activation='gelu', positional_embedding='sin', dropout=0.0)
-    m.load_state_dict(sd, strict=True)
-    return m.eval(), cond.ConditioningAttributes
+    return _build_ref_lm(cfg, sd, table)
 
 
 def golden_encodec(name, batch, length, wseed, xseed, full):
@@ -191,8 +155,70 @@ def golden_stereo():
     torch.save(out, os.path.join(H.GOLDEN_DIR, 'encodec_tiny_stereo.pt'))
 
 
+FULLSIZE_STEPS = [0, 1, 374, 749, 1124, 1499, 1502]   # teacher-forced steps kept (KV length = step + 1)
+
+
+def golden_lm_fullsize(name, batch, t_text=16, T=1500, wseed=0, cseed=3, sseed=17, topn=32):
+    """FULL-DEPTH released architectures at the benchmarked sequence length: one non-streaming causal
+    forward of the reference LMModel (fp32, CPU) over a seeded delay-pattern sequence of T frames with the CFG rows
+    [cond; null] = 2*batch, keeping the top-`topn` CFG-mixed logits at FULLSIZE_STEPS (LMModel.forward lm.py:221-268 +
+    the mix of lm.py:393-399).  Weights / conditions / tokens are regenerated from seeds by the test."""
+    import time
+    t0 = time.time()
+    cfg = synth.lm_config(name)
+    sd = synth.synth_lm_state_dict(cfg, seed=wseed)
+    _, _, cross = H.lm_condition(cfg, sd, batch, t_text, cseed)
+    m, _ = build_ref_lm(cfg, sd, {'__null__': (torch.zeros(t_text, cfg['cond_dim']), torch.zeros(t_text, dtype=torch.long))})
+    del sd
+    seq = H.fullsize_sequence(cfg, batch, T, sseed)                     # [B, K, T + K] delay-pattern sequence
+    S = seq.shape[-1]
+    ct = {'description': (cross, torch.ones(cross.shape[:2], dtype=torch.long))}
+    logits = m(torch.cat([seq, seq], 0)[..., :S - 1], conditions=[], condition_tensors=ct)   # [2B, K, S-1, card]
+    c, u = logits.split(batch, dim=0)
+    mixed = (u + (c - u) * cfg['cfg_coef'])[:, :, FULLSIZE_STEPS, :].permute(2, 0, 1, 3).contiguous()   # [n, B, K, card]
+    tv, ti = mixed.topk(topn, dim=-1)
+    out = dict(name=name, batch=batch, t_text=t_text, T=T, wseed=wseed, cseed=cseed, sseed=sseed, steps=FULLSIZE_STEPS,
+               logits_top_v=tv, logits_top_i=ti.to(torch.int16), seq_head=seq[..., :16].clone(),
+               cond_top_v=c[:, :, FULLSIZE_STEPS, :].permute(2, 0, 1, 3).gather(-1, ti), )
+    torch.save(out, os.path.join(H.GOLDEN_DIR, f'{name}_full.pt'))
+    print(name, 'fullsize logits', tuple(tv.shape), f'{time.time() - t0:.0f} s')
+
+
+def golden_encodec_fullsize():
+    """BASELINE config 1 at its real length (10 s = 240 000 samples at 24 kHz: codes [1, n_q, 750] for n_q = 8 and 32)
+    and a [2, 1, 320000] slice of config 4 (32 kHz, 4 codebooks): codes from the reference (int16 to keep the fixture small)."""
+    cfg = synth.ENCODEC_CONFIGS['encodec_24k']
+    for n_q in (8, 32):
+        c = dict(cfg)
+        c['n_q'] = n_q
+        sd = synth.synth_encodec_state_dict(c, seed=5)
+        m = build_ref_encodec(c, sd)
+        x = H.audio_input(c, 1, 240000, 6)
+        codes, scale = m.encode(x)
+        wav = m.decode(codes, scale)
+        torch.save(dict(name='encodec_24k', n_q=n_q, batch=1, length=240000, wseed=5, xseed=6, codes=codes.to(torch.int16),
+                        wav_stride=997, wav_strided=wav[..., ::997].clone(), wav_len=wav.shape[-1], x_head=x[..., :64].clone()),
+                   os.path.join(H.GOLDEN_DIR, f'encodec_24k_10s_nq{n_q}.pt'))
+        print('encodec_24k 10 s n_q', n_q, tuple(codes.shape))
+    cfg = synth.ENCODEC_CONFIGS['encodec_32k']
+    sd = synth.synth_encodec_state_dict(cfg, seed=7)
+    m = build_ref_encodec(cfg, sd)
+    x = H.audio_input(cfg, 2, 320000, 8)
+    codes, scale = m.encode(x)
+    wav = m.decode(codes, scale)
+    torch.save(dict(name='encodec_32k', batch=2, length=320000, wseed=7, xseed=8, codes=codes.to(torch.int16),
+                    wav_stride=997, wav_strided=wav[..., ::997].clone(), wav_len=wav.shape[-1], x_head=x[..., :64].clone()),
+               os.path.join(H.GOLDEN_DIR, 'encodec_32k_10s.pt'))
+    print('encodec_32k 2 x 10 s', tuple(codes.shape))
+
+
 if __name__ == '__main__':
     os.makedirs(H.GOLDEN_DIR, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'fullsize':
+        golden_encodec_fullsize()
+        golden_lm_fullsize('musicgen_medium', 8)
+        golden_lm_fullsize('musicgen_large', 4)
+        sys.exit(0)
     golden_patterns()
     golden_sampling()
     golden_encodec('encodec_tiny', 2, 1234, 1, 2, full=True)

@@ -44,3 +44,18 @@ def exp_noise(seed: int, step: int, rows: int, card: int) -> torch.Tensor:
     g = torch.Generator()
     g.manual_seed(seed * 100003 + step)
     return torch.empty(rows, card).exponential_(1, generator=g)
+
+
+def fullsize_sequence(cfg: dict, batch: int, T: int, seed: int) -> torch.Tensor:
+    """Seeded codes [B, K, T] laid out in the delay pattern (codebook k shifted by delays[k] + 1, `card` = special token
+    elsewhere): the [B, K, T + max_delay + 1] sequence LMModel.generate builds with build_pattern_sequence
+    (audiocraft/modules/codebooks_patterns.py:154-179, 339-356)."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    K, card, delays = cfg['n_q'], cfg['card'], cfg['delays']
+    codes = torch.randint(0, card, (batch, K, T), generator=g)
+    S = T + max(delays) + 1
+    seq = torch.full((batch, K, S), card, dtype=torch.long)
+    for k in range(K):
+        seq[:, k, 1 + delays[k]:1 + delays[k] + T] = codes[:, k]
+    return seq
