@@ -13,28 +13,31 @@ LIB_PATH = os.path.join(_HERE, 'libaudiocraft_b200.so')
 CONV_FP32, CONV_TF32X3, CONV_TF32X3_MMASYNC = 0, 1, 2
 CONV_T6_FLUSH = 3   # host-side selector only: layers that qualify go through the EXPERIMENTAL acb_conv1d_t6, the rest fp32
 ACB_LM_MAX_SPLIT = 8
+ACB_LM_PART_SLOTS = 16
 ACB_LM_PLAN_BYTES = 2 << 20
 
 
 class LMConfig(C.Structure):
     _fields_ = [('dim', C.c_int), ('num_heads', C.c_int), ('num_layers', C.c_int), ('ffn_dim', C.c_int),
                 ('n_q', C.c_int), ('card', C.c_int), ('cross_attention', C.c_int), ('max_rows', C.c_int),
-                ('max_seq', C.c_int), ('max_text', C.c_int), ('pos_scale', C.c_float)]
+                ('max_seq', C.c_int), ('max_text', C.c_int), ('pos_scale', C.c_float), ('positional_embedding', C.c_int)]
 
 
 class LMWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('emb', 'inv_freq', 'w_qkv', 'w_o', 'w_cq', 'w_ckv', 'w_co', 'w_ff1',
-                                           'w_ff2', 'ln', 'out_norm', 'heads')]
+                                           'w_ff2', 'ln', 'out_norm', 'heads', 'wp_qkv', 'wp_o', 'wp_cq', 'wp_co',
+                                           'wp_ff1', 'wp_ff2', 'wp_heads', 'rope_freq')]
 
 
 class LMBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('x', 'h16', 'a16', 'f16', 'q32', 'part', 'logits', 'k_cache', 'v_cache',
-                                           'ck_cache', 'cv_cache', 'cross16', 'seq', 'seq_mask', 'pos', 'noise', 'plan')]
+                                           'ck_cache', 'cv_cache', 'cross16', 'seq', 'seq_mask', 'pos', 'noise', 'plan',
+                                           'stats', 'bar')]
 
 
 class LMSampling(C.Structure):
     _fields_ = [('use_sampling', C.c_int), ('temp', C.c_float), ('top_k', C.c_int), ('top_p', C.c_float),
-                ('cfg_coef', C.c_float), ('seed', C.c_uint64), ('noise_from_buffer', C.c_int)]
+                ('cfg_coef', C.c_float), ('seed', C.c_uint64), ('noise_from_buffer', C.c_int), ('cfg_coef_beta', C.c_float)]
 
 
 _lib = None
@@ -71,6 +74,8 @@ def lib():
     L.acb_lm_step_logits.argtypes = [vp, vp, vp]
     L.acb_lm_launches_per_step.argtypes = [vp]
     L.acb_lm_rows_pad.argtypes = [ci]
+    L.acb_lm_pack_weight.argtypes = [vp, vp, ci, ci, vp]
+    L.acb_lm_debug_step_plan.argtypes = [vp, C.POINTER(ci)]
     L.acb_lm_uses_pdl.argtypes = [vp]
     L.acb_lm_debug_gemms.argtypes = [vp, vp, C.POINTER(ci)]
     L.acb_sample.argtypes = [vp, vp, vp, ci, ci, ci, ci, C.POINTER(LMSampling), C.c_uint64, vp]
@@ -80,7 +85,7 @@ def lib():
                  'acb_rvq_decode', 'acb_lm_create', 'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps',
                  'acb_lm_step_logits', 'acb_lm_launches_per_step', 'acb_lm_rows_pad', 'acb_sample',
                  'acb_device_sm_count', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_debug_chain_latency',
-                 'acb_conv1d_t6', 'acb_conv1d_t6_tile', 'acb_debug_grid_barrier'):
+                 'acb_conv1d_t6', 'acb_conv1d_t6_tile', 'acb_debug_grid_barrier', 'acb_lm_pack_weight', 'acb_lm_debug_step_plan'):
         getattr(L, name).restype = ci
     _lib = L
     return L
@@ -91,7 +96,7 @@ EXPORTS = ['acb_version', 'acb_last_error', 'acb_device_sm_count', 'acb_weight_n
            'acb_lstm_recurrent', 'acb_lstm_state_bytes', 'acb_rvq_encode', 'acb_rvq_decode', 'acb_lm_create',
            'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps', 'acb_lm_step_logits', 'acb_lm_rows_pad',
            'acb_lm_launches_per_step', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_sample', 'acb_debug_chain_latency', 'acb_conv1d_t6', 'acb_conv1d_t6_tile',
-           'acb_debug_grid_barrier']
+           'acb_debug_grid_barrier', 'acb_lm_pack_weight', 'acb_lm_debug_step_plan']
 
 
 def check(rc: int, what: str = ''):

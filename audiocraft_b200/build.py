@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libaudiocraft_b200.so')
 STAMP = LIB + '.stamp'
-SOURCES = ['api.cu', 'encodec.cu', 'lm.cu', 'lm_probe.cu']
-HEADERS = ['common.cuh', 'gridbar.cuh', os.path.join('..', '..', 'include', 'audiocraft_b200.h')]
+SOURCES = ['api.cu', 'encodec.cu', 'lm.cu', 'lm_step.cu', 'lm_probe.cu']
+HEADERS = ['common.cuh', 'gridbar.cuh', 'lm_step.cuh', os.path.join('..', '..', 'include', 'audiocraft_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC',
          '-Xptxas', '-v']

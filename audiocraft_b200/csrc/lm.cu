@@ -17,6 +17,7 @@
 //     generate() instead of every step (the reference recomputes them, transformer.py:355-357).
 //   * attention for one query token: one CTA per (row, head) streaming K then V with 128-bit loads.
 #include "common.cuh"
+#include "lm_step.cuh"
 #include <math.h>
 #include <new>
 #include <vector>
@@ -919,6 +920,7 @@ struct SampleParams {
     int64_t* tokens;      // [batch][n_q] stand-alone output (may be NULL)
     int batch, rows, n_q, card, NP;
     int use_sampling, top_k; float temp, top_p, cfg_coef; uint64_t seed; uint32_t step;
+    float cfg_coef_beta;   // rows == 3 * batch: double CFG (lm.py:362-376)
 };
 
 // descending order, ties by ascending index
@@ -935,9 +937,10 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
     __shared__ float s_scalar;
     const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
     const int card = p.card;
-    const bool cfg = p.rows == 2 * p.batch;
+    const bool cfg = p.rows == 2 * p.batch, cfg3 = p.rows == 3 * p.batch;   // [cond; null] or [cond; style-only; null]
     const float* lc = p.logits + ((size_t)b * p.n_q + k) * card;
-    const float* lu = p.logits + ((size_t)(p.batch + b) * p.n_q + k) * card;
+    const float* lu = p.logits + ((size_t)((cfg3 ? 2 : 1) * p.batch + b) * p.n_q + k) * card;
+    const float* lw = p.logits + ((size_t)(p.batch + b) * p.n_q + k) * card;
     pdl_trigger();
     pdl_wait();
     const int cur_pos = p.pos ? p.pos[0] : 0;   // read once: the last block to finish advances it (below)
@@ -946,6 +949,7 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
     for (int i = tid; i < card; i += nt) {
         float l = lc[i];
         if (cfg) { float u = lu[i]; l = u + (l - u) * p.cfg_coef; }   // lm.py:399
+        else if (cfg3) { const float u = lu[i], w = lw[i]; l = u + p.cfg_coef * (w + p.cfg_coef_beta * (l - w) - u); }   // lm.py:372-376
         pr[i] = l;
         if (p.logits_out) p.logits_out[((size_t)b * p.n_q + k) * card + i] = l;
     }
@@ -1327,6 +1331,9 @@ struct acb_lm {
     bool pdl = true;          // programmatic dependent launch between the kernels of a step
     bool wide = false;        // ACB_LM_STEP=v6: wide cluster GEMMs with LayerNorm folded in (8 kernels/layer; measured slower)
     bool chain = false;       // GEMM/LN phases between attention kernels run in persistent chain kernels (opt-in)
+    bool fused = false;       // the whole transformer of a step is ONE persistent kernel (lm_step.cu); default when the packed weights are given
+    StepLaunch step{};
+    unsigned long long* trace = nullptr;   // ACB_LM_STEP_TRACE=1: per-phase %globaltimer stamps of CTA 0
     int chain_grid = 0, chain_slab = 0;
     size_t chain_smem = 0;
     std::vector<ChainPhase> plan;            // host copy of every chain's phases, in launch order
@@ -1717,7 +1724,7 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         while (NP < c.card) NP <<= 1;
         SampleParams sp{B.logits, lm->samp.noise_from_buffer ? B.noise : nullptr, logits_out, B.seq, B.seq_mask, B.pos,
                         c.max_seq, nullptr, lm->batch, rows, c.n_q, c.card, NP, lm->samp.use_sampling, lm->samp.top_k,
-                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0};
+                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0, lm->samp.cfg_coef_beta};
         size_t smem = ((size_t)c.card + 2 * (size_t)NP) * sizeof(float);
         ACB_LAUNCH(lm_sample_kernel, dim3(c.n_q, lm->batch), dim3(1024), smem, s, pdl, sp);
         ++nl;
@@ -1907,7 +1914,7 @@ static int enqueue_step_wide(acb_lm* lm, cudaStream_t s, float* logits_out, int*
         while (NP < c.card) NP <<= 1;
         SampleParams sp{B.logits, lm->samp.noise_from_buffer ? B.noise : nullptr, logits_out, B.seq, B.seq_mask, B.pos,
                         c.max_seq, nullptr, lm->batch, rows, c.n_q, c.card, NP, lm->samp.use_sampling, lm->samp.top_k,
-                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0};
+                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0, lm->samp.cfg_coef_beta};
         size_t smem = ((size_t)c.card + 2 * (size_t)NP) * sizeof(float);
         ACB_LAUNCH(lm_sample_kernel, dim3(c.n_q, lm->batch), dim3(1024), smem, s, pdl, sp);
         ++nl;
@@ -1968,7 +1975,30 @@ static int enqueue_step_chain(acb_lm* lm, cudaStream_t s, float* logits_out, int
         while (NP < c.card) NP <<= 1;
         SampleParams sp{B.logits, lm->samp.noise_from_buffer ? B.noise : nullptr, logits_out, B.seq, B.seq_mask, B.pos,
                         c.max_seq, nullptr, lm->batch, rows, c.n_q, c.card, NP, lm->samp.use_sampling, lm->samp.top_k,
-                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0};
+                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0, lm->samp.cfg_coef_beta};
+        size_t smem = ((size_t)c.card + 2 * (size_t)NP) * sizeof(float);
+        ACB_LAUNCH(lm_sample_kernel, dim3(c.n_q, lm->batch), dim3(1024), smem, s, false, sp);
+        ++nl;
+        DBG("lm_sample_kernel", -1);
+    }
+    if (n_launch) *n_launch = nl;
+    return ACB_OK;
+}
+
+// Fused step: [memset of the barrier counter] -> lm_step_kernel (embed ... logits) -> lm_sample_kernel.
+static int enqueue_step_fused(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool step_only, bool capturing) {
+    const acb_lm_config& c = lm->cfg;
+    const acb_lm_buffers& B = lm->buf;
+    int nl = 0;
+    ACB_TRY(lm_step_launch(lm->step, s));
+    ++nl;
+    DBG("lm_step_kernel", -1);
+    if (!step_only) {
+        int NP = 1;
+        while (NP < c.card) NP <<= 1;
+        SampleParams sp{B.logits, lm->samp.noise_from_buffer ? B.noise : nullptr, logits_out, B.seq, B.seq_mask, B.pos,
+                        c.max_seq, nullptr, lm->batch, lm->rows, c.n_q, c.card, NP, lm->samp.use_sampling, lm->samp.top_k,
+                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0, lm->samp.cfg_coef_beta};
         size_t smem = ((size_t)c.card + 2 * (size_t)NP) * sizeof(float);
         ACB_LAUNCH(lm_sample_kernel, dim3(c.n_q, lm->batch), dim3(1024), smem, s, false, sp);
         ++nl;
@@ -1980,6 +2010,7 @@ static int enqueue_step_chain(acb_lm* lm, cudaStream_t s, float* logits_out, int
 
 static int enqueue_step(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only = false,
                         bool capturing = false) {
+    if (lm->fused) return enqueue_step_fused(lm, s, logits_out, n_launch, gemms_only, capturing);
     if (lm->chain) return enqueue_step_chain(lm, s, logits_out, n_launch, gemms_only, capturing);
     return lm->wide ? enqueue_step_wide(lm, s, logits_out, n_launch, gemms_only, capturing)
                     : enqueue_step_kernels(lm, s, logits_out, n_launch, gemms_only, capturing);
@@ -2036,6 +2067,7 @@ extern "C" int acb_lm_destroy(acb_lm_t* lm) {
     drop_graph(lm);
     if (lm->capture_stream) cudaStreamDestroy(lm->capture_stream);
     if (lm->timing) cudaFree(lm->timing);
+    if (lm->trace) cudaFree(lm->trace);
     delete lm;
     return ACB_OK;
 }
@@ -2044,7 +2076,7 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
                             const acb_lm_sampling* sampling, void* stream) {
     ACB_REQUIRE(lm && sampling, "acb_lm_begin: null argument");
     const acb_lm_config& c = lm->cfg;
-    ACB_REQUIRE(batch >= 1 && (rows == batch || rows == 2 * batch), "acb_lm_begin: rows must be batch or 2*batch");
+    ACB_REQUIRE(batch >= 1 && (rows == batch || rows == 2 * batch || rows == 3 * batch), "acb_lm_begin: rows must be batch, 2*batch (CFG) or 3*batch (double CFG)");
     ACB_REQUIRE(rows <= c.max_rows, "acb_lm_begin: rows %d > max_rows %d", rows, c.max_rows);
     ACB_REQUIRE(seq_len >= 2 && seq_len <= c.max_seq, "acb_lm_begin: seq_len %d > max_seq %d", seq_len, c.max_seq);
     ACB_REQUIRE(!c.cross_attention || cross, "acb_lm_begin: the model has cross attention, a condition tensor is required"
@@ -2097,6 +2129,18 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
         }
         const char* ev = getenv("ACB_LM_STEP");
         lm->wide = ev && ev[0] == 'v' && ev[1] == '6';
+        // default: the persistent fused step (needs the packed weights); ACB_LM_STEP=v5 selects one kernel per phase
+        lm->fused = lm->w.wp_qkv != nullptr && !(ev && ev[0] == 'v');
+        ACB_REQUIRE(c.positional_embedding == 0 || lm->fused, "acb_lm_begin: rotary positions are built in the fused decode step only");
+        if (lm->fused) {
+            ACB_TRY(lm_step_prepare(c, lm->w, lm->buf, rows, batch, text_len, lm->has_cross, lm->sms, &lm->step));
+            if (env_int("ACB_LM_COOP", 1) == 0) lm->step.cooperative = false;
+            if (env_int("ACB_LM_STEP_TRACE", 0)) {
+                if (!lm->trace) ACB_CHECK_CUDA(cudaMalloc(&lm->trace, 4096 * sizeof(unsigned long long)));
+                ACB_CHECK_CUDA(cudaMemset(lm->trace, 0, 4096 * sizeof(unsigned long long)));
+                ACB_REQUIRE(lm->step.n_phases + 2 <= 4096, "trace buffer too small");
+            }
+        }
         const char* ec = getenv("ACB_LM_CHAIN");
         lm->chain = (ec && ec[0] == '1') && lm->buf.plan != nullptr;
         if (lm->chain) ACB_TRY(build_chain_plan(lm, s));
@@ -2126,6 +2170,7 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
         if (rc == ACB_OK && e == cudaSuccess) return ACB_OK;
         cudaGetLastError();
         drop_graph(lm);
+        if (lm->fused && lm->step.cooperative && attempt == 0) { lm->step.cooperative = false; continue; }   // plain launch (grid = #SMs is co-resident anyway)
         if (!lm->pdl || attempt == 1) {
             if (rc == ACB_OK) acb_set_error("acb_lm_begin: graph capture failed: %s", cudaGetErrorString(e));
             return rc != ACB_OK ? rc : ACB_ERR_CUDA;
@@ -2202,9 +2247,39 @@ static int report_timeline(acb_lm* lm, cudaStream_t s) {
     return ACB_OK;
 }
 
+// ACB_LM_STEP_TRACE=1: time between consecutive grid barriers of the fused step as seen by CTA 0 (ns), summed per phase kind.
+static int report_step_trace(acb_lm* lm, cudaStream_t s) {
+    ACB_CHECK_CUDA(cudaStreamSynchronize(s));
+    const int n = lm->step.n_phases;
+    std::vector<unsigned long long> h((size_t)n + 1);
+    ACB_CHECK_CUDA(cudaMemcpy(h.data(), lm->trace, ((size_t)n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const bool cross = lm->has_cross;
+    const int per = cross ? 12 : 8;
+    static const char* names_c[12] = {"qkv", "attn", "o", "res1", "cq", "xattn", "co", "res2", "ff1", "gelu", "ff2", "res3"};
+    static const char* names_n[8] = {"qkv", "attn", "o", "res1", "ff1", "gelu", "ff2", "res3"};
+    double sum[12] = {0}, mx[12] = {0};
+    for (int l = 0; l < lm->cfg.num_layers; ++l)
+        for (int k = 0; k < per; ++k) {
+            const int i = 1 + l * per + k;     // stamp i is taken after barrier i; phase k of layer l ends at barrier 1 + l*per + k + 1
+            if (i + 1 >= n || !h[i] || !h[i + 1]) continue;
+            const double dt = (double)(h[i + 1] - h[i]);
+            sum[k] += dt; if (dt > mx[k]) mx[k] = dt;
+        }
+    fprintf(stderr, "[acb step trace] rows=%d pos=? total %.1f us (kernel start -> last barrier); embed %.2f us; per-layer mean (max) us:",
+            lm->rows, (double)(h[n - 1] - h[0]) * 1e-3, (double)(h[1] - h[0]) * 1e-3);
+    for (int k = 0; k < per; ++k)
+        fprintf(stderr, "  %s %.2f (%.2f)", cross ? names_c[k] : names_n[k], sum[k] * 1e-3 / lm->cfg.num_layers, mx[k] * 1e-3);
+    fprintf(stderr, "\n");
+    ACB_CHECK_CUDA(cudaMemset(lm->trace, 0, 4096 * sizeof(unsigned long long)));
+    return ACB_OK;
+}
+
 extern "C" int acb_lm_step_logits(acb_lm_t* lm, float* logits_out, void* stream) {
     ACB_REQUIRE(lm && lm->rows > 0, "acb_lm_step_logits: call acb_lm_begin first");
+    if (lm->fused && lm->trace) lm->step.p.trace = lm->trace;
     ACB_TRY(enqueue_step(lm, (cudaStream_t)stream, logits_out, nullptr));
+    if (lm->fused && lm->trace) { lm->step.p.trace = nullptr; ACB_TRY(report_step_trace(lm, (cudaStream_t)stream)); }
+    if (lm->fused) return ACB_OK;
     if (lm->timing && !lm->wide && !lm->chain) ACB_TRY(report_timeline(lm, (cudaStream_t)stream));
     if (lm->timing && lm->wide && !lm->chain) ACB_TRY(report_timing(lm, (cudaStream_t)stream));
     return ACB_OK;
@@ -2215,19 +2290,32 @@ extern "C" int acb_lm_debug_gemms(acb_lm_t* lm, void* stream, int* n_launches) {
     return enqueue_step(lm, (cudaStream_t)stream, nullptr, n_launches, true);
 }
 
-extern "C" int acb_lm_rows_pad(int rows) { return 8 * nt_for_rows(rows); }
+extern "C" int acb_lm_debug_step_plan(const acb_lm_t* lm, int* out) {
+    ACB_REQUIRE(lm && out && lm->fused, "acb_lm_debug_step_plan: the fused step is not active");
+    for (int i = 0; i < ACB_STEP_GEMMS; ++i) {
+        const StepGemm& g = lm->step.p.g[i];
+        out[4 * i] = g.N; out[4 * i + 1] = g.K; out[4 * i + 2] = g.ksplit; out[4 * i + 3] = g.kb_per;
+    }
+    out[4 * ACB_STEP_GEMMS] = lm->step.p.n_stage;
+    out[4 * ACB_STEP_GEMMS + 1] = lm->step.p.R;
+    out[4 * ACB_STEP_GEMMS + 2] = lm->step.n_phases;
+    out[4 * ACB_STEP_GEMMS + 3] = (int)lm->step.smem;
+    return ACB_OK;
+}
+
+extern "C" int acb_lm_rows_pad(int rows) { return rows <= 16 ? 16 : 8 * nt_for_rows(rows); }
 
 extern "C" int acb_lm_launches_per_step(const acb_lm_t* lm) { return lm ? lm->launches : 0; }
 
 extern "C" int acb_sample(const float* logits, const float* noise, int64_t* tokens, int batch, int rows, int n_q, int card,
                           const acb_lm_sampling* sampling, uint64_t step, void* stream) {
     ACB_REQUIRE(logits && tokens && sampling, "acb_sample: null argument");
-    ACB_REQUIRE(batch >= 1 && (rows == batch || rows == 2 * batch) && n_q >= 1 && card >= 2 && card <= 4096, "acb_sample: bad shape");
+    ACB_REQUIRE(batch >= 1 && (rows == batch || rows == 2 * batch || rows == 3 * batch) && n_q >= 1 && card >= 2 && card <= 4096, "acb_sample: bad shape");
     int NP = 1;
     while (NP < card) NP <<= 1;
     SampleParams sp{logits, sampling->noise_from_buffer ? noise : nullptr, nullptr, nullptr, nullptr, nullptr, 0, tokens, batch, rows, n_q, card, NP,
                     sampling->use_sampling, sampling->top_k, sampling->temp, sampling->top_p, sampling->cfg_coef,
-                    sampling->seed, (uint32_t)step};
+                    sampling->seed, (uint32_t)step, sampling->cfg_coef_beta};
     size_t smem = ((size_t)card + 2 * (size_t)NP) * sizeof(float);
     if (smem > 48 * 1024)
         ACB_CHECK_CUDA(cudaFuncSetAttribute(lm_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

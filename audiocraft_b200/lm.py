@@ -94,10 +94,46 @@ class LMModel:
         w['ln'] = ln
         w['out_norm'] = torch.stack([sd['out_norm.weight'].float(), sd['out_norm.bias'].float()]).to(dev).contiguous()
         w['heads'] = torch.cat([h(sd[f'linears.{k}.weight']) for k in range(self.n_q)], dim=0).contiguous()
+        # the persistent fused step streams 128 x 64 tiles in the tensor-core operand layout: re-pack once at load time
+        # (acb_lm_pack_weight); shapes that do not tile (N % 128, K % 64) keep the per-phase kernels
+        ffn, NH = self.ffn_dim, self.n_q * self.card
+        self.fused_ok = d % 128 == 0 and ffn % 128 == 0 and NH % 128 == 0
+        if self.fused_ok:
+            def pack(name, n, k):
+                src = w[name]
+                if src is None:
+                    return None
+                dst = torch.empty_like(src)
+                layers = 1 if src.dim() == 2 else src.shape[0]
+                for li in range(layers):
+                    _lib.check(self._lib.acb_lm_pack_weight(src[li].data_ptr() if src.dim() == 3 else src.data_ptr(),
+                                                            dst[li].data_ptr() if dst.dim() == 3 else dst.data_ptr(), n, k,
+                                                            _lib.stream()), 'lm_pack_weight')
+                return dst
+            w['wp_qkv'] = pack('w_qkv', 3 * d, d)
+            w['wp_o'] = pack('w_o', d, d)
+            w['wp_cq'] = pack('w_cq', d, d)
+            w['wp_co'] = pack('w_co', d, d)
+            w['wp_ff1'] = pack('w_ff1', ffn, d)
+            w['wp_ff2'] = pack('w_ff2', d, ffn)
+            w['wp_heads'] = pack('heads', NH, d)
+        else:
+            for n in ('wp_qkv', 'wp_o', 'wp_cq', 'wp_co', 'wp_ff1', 'wp_ff2', 'wp_heads'):
+                w[n] = None
+        # positional_embedding (transformer.py:632-637): rotary frequencies computed by the same torch ops as rope.py:68-69
+        self.positional_embedding = cfg.get('positional_embedding', 'sin')
+        assert self.positional_embedding in ('sin', 'rope', 'sin_rope')
+        if self.positional_embedding != 'sin':
+            if not self.fused_ok:
+                raise NotImplementedError("rotary positions need the fused decode step (dim, ffn, n_q*card multiples of 128)")
+            adim2 = torch.arange(0, 64, 2, dtype=torch.float32)[:32]
+            w['rope_freq'] = (1.0 / (float(cfg['max_period']) ** (adim2 / 64))).to(dev).contiguous()
+        else:
+            w['rope_freq'] = None
         self._w = w
         self.weight_bytes_per_step = sum(
             t.numel() * t.element_size() for k, t in w.items()
-            if t is not None and k not in ('emb', 'inv_freq', 'w_ckv'))
+            if t is not None and k not in ('emb', 'inv_freq', 'w_ckv') and not k.startswith('wp_') and k != 'rope_freq')
 
     # ------------------------------------------------------------------ reference attributes
     @property
@@ -133,7 +169,9 @@ class LMModel:
         b['a16'] = torch.zeros((rp, d), device=dev, dtype=f16)
         b['f16'] = torch.zeros((rp, self.ffn_dim), device=dev, dtype=f16)
         b['q32'] = torch.zeros((rp, d), device=dev, dtype=f32)
-        b['part'] = torch.zeros((_lib.ACB_LM_MAX_SPLIT, rp, d), device=dev, dtype=f32)
+        b['part'] = torch.zeros((_lib.ACB_LM_PART_SLOTS, rp, max(3 * d, self.ffn_dim, self.n_q * self.card)), device=dev, dtype=f32)
+        b['stats'] = torch.zeros((8, rp, 2), device=dev, dtype=f32)
+        b['bar'] = torch.zeros(32, device=dev, dtype=torch.int32)
         b['logits'] = torch.zeros((rp, self.n_q * self.card), device=dev, dtype=f32)
         b['k_cache'] = torch.zeros((L, max_rows, H, max_seq, 64), device=dev, dtype=f16)
         b['v_cache'] = torch.zeros((L, max_rows, H, max_seq, 64), device=dev, dtype=f16)
@@ -152,12 +190,14 @@ class LMModel:
         self._bufs = b
         cfg = _lib.LMConfig(self.dim, self.num_heads, self.num_layers, self.ffn_dim, self.n_q, self.card,
                             int(self.cross_attention), max_rows, max_seq, max_text,
-                            float(self.cfg_dict.get('positional_scale', 1.0)))
+                            float(self.cfg_dict.get('positional_scale', 1.0)),
+                            {'sin': 0, 'rope': 1, 'sin_rope': 2}[self.positional_embedding])
         wts = _lib.LMWeights(*[_lib.ptr(self._w[n]) for n in ('emb', 'inv_freq', 'w_qkv', 'w_o', 'w_cq', 'w_ckv',
-                                                              'w_co', 'w_ff1', 'w_ff2', 'ln', 'out_norm', 'heads')])
+                                                              'w_co', 'w_ff1', 'w_ff2', 'ln', 'out_norm', 'heads', 'wp_qkv',
+                                                              'wp_o', 'wp_cq', 'wp_co', 'wp_ff1', 'wp_ff2', 'wp_heads', 'rope_freq')])
         bufs = _lib.LMBuffers(*[_lib.ptr(b[n]) for n in ('x', 'h16', 'a16', 'f16', 'q32', 'part', 'logits', 'k_cache',
                                                          'v_cache', 'ck_cache', 'cv_cache', 'cross16', 'seq',
-                                                         'seq_mask', 'pos', 'noise', 'plan')])
+                                                         'seq_mask', 'pos', 'noise', 'plan', 'stats', 'bar')])
         handle = C.c_void_p()
         _lib.check(self._lib.acb_lm_create(C.byref(cfg), C.byref(wts), C.byref(bufs), C.byref(handle)), 'lm_create')
         self._handle = handle
@@ -178,11 +218,18 @@ class LMModel:
 
     # ------------------------------------------------------------------ conditions (lm.py:488-511)
     def _prepare_conditions(self, conditions, two_step_cfg, cfg_coef_beta):
-        if cfg_coef_beta is not None:
-            raise NotImplementedError("double CFG (cfg_coef_beta, MusicGen-Style) is not built on the B200 path")
         if not conditions:
             return None
         assert self.condition_provider is not None, "conditions given but the model has no condition_provider"
+        if cfg_coef_beta is not None:
+            # lm.py:490-496: [conditions; conditions without their description; null conditions].  The style-only rows need
+            # a 'self_wav' conditioner (conditioners.py:231-234 asserts the same); it is a front-end outside the hot path,
+            # so double CFG is reachable with a pre-computed 3B-row `cross_attention_src`.
+            for c in conditions:
+                assert 'description' in c.text and 'self_wav' in getattr(c, 'wav', {}), \
+                    "double CFG needs 'description' and 'self_wav' conditions (conditioners.py:231-234)"
+            raise NotImplementedError("style (self_wav) conditioner front-end is not built; pass cross_attention_src with "
+                                      "[cond; style-only; null] rows")
         null_conditions = nullify_all(conditions)
         tokenized = self.condition_provider.tokenize(list(conditions) + null_conditions)
         tensors = self.condition_provider(tokenized)
@@ -240,7 +287,10 @@ class LMModel:
             if cross is not None:
                 cross = cross.to(self.device, torch.float32).contiguous()
                 assert cross.dim() == 3 and cross.shape[2] == self.dim
-                assert cross.shape[0] in (B, 2 * B), "condition rows must be B (no CFG) or 2B ([cond; null])"
+                assert cross.shape[0] in (B, 2 * B, 3 * B), \
+                    "condition rows must be B (no CFG), 2B ([cond; null]) or 3B ([cond; style-only; null], double CFG)"
+                assert (cross.shape[0] == 3 * B) == (cfg_coef_beta is not None), \
+                    "cfg_coef_beta goes with 3B condition rows (lm.py:362-376)"
                 rows, text_len = cross.shape[0], cross.shape[1]
             self._ensure(rows, S, text_len, B)
             bufs = self._bufs
@@ -248,7 +298,8 @@ class LMModel:
             bufs['seq_mask'][:, :S] = mask.to(torch.uint8)
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             samp = _lib.LMSampling(int(bool(use_sampling)), float(temp), int(top_k), float(top_p), float(coef), seed,
-                                   1 if self._debug_noise_fn is not None else 0)
+                                   1 if self._debug_noise_fn is not None else 0,
+                                   float(cfg_coef_beta) if cfg_coef_beta is not None else 0.0)
             _lib.check(self._lib.acb_lm_begin(self._handle, _lib.ptr(cross), B, rows, text_len, S, C.byref(samp),
                                               _lib.stream()), 'lm_begin')
             self.launches_per_step = self._lib.acb_lm_launches_per_step(self._handle)
@@ -277,6 +328,81 @@ class LMModel:
             assert (out_codes >= 0).all() and (out_codes <= self.card).all()
             self.last_sequence = gen_sequence
             return out_codes
+
+    # ------------------------------------------------------------------ streaming-state surface (modules/streaming.py:59-119)
+    # The reference keeps `past_keys` / `past_values` ([rows, H, t, 64], transformer.py:266-298) per attention module and
+    # `offsets` per transformer, reachable through StreamingModule.get/set_streaming_state; LMModel._sample_next_token uses
+    # them to run two_step_cfg (lm.py:376-391).  Here the same observable state lives in the device KV cache + the device
+    # position counter; the methods below expose it under the reference's key names.
+    def streaming_begin(self, batch: int, cross: tp.Optional[torch.Tensor], max_len: int, cfg_coef: tp.Optional[float] = None,
+                        cfg_coef_beta: tp.Optional[float] = None, **sampling):
+        """Enter streaming mode for `batch` items (what `with lm.streaming():` + the first forward do in the reference):
+        allocates / resets the caches, precomputes the cross-attention K/V of `cross` ([rows,T,d] rows = batch, 2*batch or
+        3*batch) and captures the step graph.  Then `streaming_step(tokens)` consumes one [B,K] column per call."""
+        with torch.cuda.device(self.device):
+            rows, text_len = batch, 0
+            if cross is not None:
+                cross = cross.to(self.device, torch.float32).contiguous()
+                rows, text_len = cross.shape[0], cross.shape[1]
+            self._ensure(rows, max_len + 1, text_len, batch)
+            b = self._bufs
+            b['seq'][:batch].fill_(-1)
+            b['seq_mask'].fill_(1)
+            samp = _lib.LMSampling(int(bool(sampling.get('use_sampling', False))), float(sampling.get('temp', 1.0)),
+                                   int(sampling.get('top_k', 0)), float(sampling.get('top_p', 0.0)),
+                                   float(self.cfg_coef if cfg_coef is None else cfg_coef), int(sampling.get('seed', 0)), 0,
+                                   float(cfg_coef_beta) if cfg_coef_beta is not None else 0.0)
+            _lib.check(self._lib.acb_lm_begin(self._handle, _lib.ptr(cross), batch, rows, text_len, max_len + 1, C.byref(samp),
+                                              _lib.stream()), 'lm_begin')
+            self._stream = dict(batch=batch, rows=rows, max_len=max_len)
+
+    @torch.no_grad()
+    def streaming_step(self, tokens: torch.Tensor) -> torch.Tensor:
+        """LMModel.forward on ONE column in streaming mode (lm.py:221-268 with S = 1): tokens [B,K] -> CFG-mixed logits
+        [B,K,card]; the KV cache grows by one position."""
+        st = self._stream
+        with torch.cuda.device(self.device):
+            pos = int(self._bufs['pos'][0].item())
+            assert pos < st['max_len'], "streaming_begin(max_len) exceeded"
+            self._bufs['seq'][:st['batch'], :, pos] = tokens.to(self.device, torch.long)
+            self._bufs['seq'][:st['batch'], :, pos + 1] = -1
+            out = torch.empty((st['batch'], self.n_q, self.card), device=self.device, dtype=torch.float32)
+            _lib.check(self._lib.acb_lm_step_logits(self._handle, out.data_ptr(), _lib.stream()), 'lm_step_logits')
+            return out
+
+    def get_streaming_state(self) -> tp.Dict[str, torch.Tensor]:
+        """StreamingModule.get_streaming_state (streaming.py:72-84) under the reference's key names: a COPY of the cached
+        keys / values of every layer up to the current offset and the per-row offsets."""
+        st, b = self._stream, self._bufs
+        pos = int(b['pos'][0].item())
+        rows = st['rows']
+        state = {'transformer.offsets': torch.full((rows,), pos, dtype=torch.long, device=self.device)}
+        for li in range(self.num_layers):
+            state[f'transformer.layers.{li}.self_attn.past_keys'] = b['k_cache'][li, :rows, :, :pos].clone()
+            state[f'transformer.layers.{li}.self_attn.past_values'] = b['v_cache'][li, :rows, :, :pos].clone()
+        return state
+
+    def set_streaming_state(self, state: tp.Dict[str, torch.Tensor]):
+        """StreamingModule.set_streaming_state (streaming.py:86-103): restore offsets and cached keys / values."""
+        st, b = self._stream, self._bufs
+        rows = st['rows']
+        offs = state['transformer.offsets']
+        assert bool((offs == offs[0]).all()), "rows of one generate() share their offset"
+        pos = int(offs[0].item())
+        state = dict(state)
+        state.pop('transformer.offsets')
+        for li in range(self.num_layers):
+            k = state.pop(f'transformer.layers.{li}.self_attn.past_keys')
+            v = state.pop(f'transformer.layers.{li}.self_attn.past_values')
+            assert k.shape == (rows, self.num_heads, pos, 64) and v.shape == k.shape, (k.shape, pos)
+            b['k_cache'][li, :rows, :, :pos] = k
+            b['v_cache'][li, :rows, :, :pos] = v
+        assert len(state) == 0, list(state.keys())
+        b['pos'][0] = pos
+
+    def reset_streaming(self):
+        """StreamingModule.reset_streaming (streaming.py:64-70): forget the cached positions."""
+        self._bufs['pos'][0] = 0
 
     @torch.no_grad()
     def teacher_forced_logits(self, sequence: torch.Tensor, cross: tp.Optional[torch.Tensor], cfg_coef: float,

@@ -130,6 +130,8 @@ typedef struct {
     int max_seq;      /* S = T + max_delay + 1, KV cache length */
     int max_text;     /* cross-attention source length the cross KV cache is sized for */
     float pos_scale;  /* positional_scale */
+    int positional_embedding; /* 0 'sin' (released MusicGen), 1 'rope', 2 'sin_rope'  (modules/transformer.py:632-637, 701-705).
+                                 rope needs the fused step (packed weights) */
 } acb_lm_config;
 
 /* fp16 matrices in the reference's own [out_features][in_features] layout, stacked over layers. */
@@ -146,16 +148,27 @@ typedef struct {
     const float* ln;      /* [L][6][d] fp32: norm1.w, norm1.b, norm_cross.w, norm_cross.b, norm2.w, norm2.b */
     const float* out_norm;/* [2][d] fp32 */
     const void* heads;    /* [n_q*card][d] fp16  LMModel.linears, lm.py:172 */
+    /* The same matrices re-packed by acb_lm_pack_weight (one call per [N][K] matrix, layers stacked) for the persistent
+     * fused decode step: 128-feature x 64-K tiles in the canonical K-major tensor-core layout, one contiguous 16 KB bulk
+     * copy each.  All NULL: the step runs as one kernel per phase (the round-1 path). */
+    const void* wp_qkv;   /* [L][3d*d] */
+    const void* wp_o;     /* [L][d*d] */
+    const void* wp_cq;    /* [L][d*d] */
+    const void* wp_co;    /* [L][d*d] */
+    const void* wp_ff1;   /* [L][ffn*d] */
+    const void* wp_ff2;   /* [L][d*ffn] */
+    const void* wp_heads; /* [n_q*card*d] */
+    const float* rope_freq; /* [32] fp32: 1 / max_period^(2i/64), RotaryEmbedding.frequencies rope.py:68-69 (NULL without rope) */
 } acb_lm_weights;
 
-/* Caller-owned state; sizes in elements.  rows_pad = max_rows rounded up to 8. */
+/* Caller-owned state; sizes in elements.  rows_pad = acb_lm_rows_pad(max_rows) (a multiple of 16). */
 typedef struct {
     float* x;          /* [rows_pad][d]            residual stream */
     void* h16;         /* [rows_pad][d] fp16       LayerNorm output / GEMM input */
     void* a16;         /* [rows_pad][d] fp16       attention output */
     void* f16;         /* [rows_pad][ffn] fp16     gelu(linear1) */
     float* q32;        /* [rows_pad][d]            self-attention queries */
-    float* part;       /* [ACB_LM_MAX_SPLIT][rows_pad][d]  split-K partial sums */
+    float* part;       /* [ACB_LM_PART_SLOTS][rows_pad][max(3d, ffn, n_q*card)]  split-K partial sums */
     float* logits;     /* [rows_pad][n_q*card] */
     void* k_cache;     /* [L][max_rows][H][max_seq][64] fp16 */
     void* v_cache;     /* same */
@@ -166,11 +179,13 @@ typedef struct {
     uint8_t* seq_mask; /* [n_q][max_seq]     pattern validity mask (codebooks_patterns.py:130-152) */
     int32_t* pos;      /* [4] device ints: pos (tokens in the KV cache), rows, batch, text_len */
     float* noise;      /* [B][n_q][card] Exponential(1) noise, read when sampling.noise_from_buffer != 0 */
-    void* plan;        /* ACB_LM_PLAN_BYTES of scratch: phase lists + grid-barrier counters of the persistent chain
-                          kernels (NULL: every phase is its own kernel) */
+    void* plan;        /* ACB_LM_PLAN_BYTES of scratch (split-KV attention records of the per-phase path) */
+    float* stats;      /* [8][rows_pad][2]  LayerNorm (mean, M2) records per d/8 columns (fused step) */
+    void* bar;         /* 128 B: grid-barrier counter of the fused step */
 } acb_lm_buffers;
 
 #define ACB_LM_MAX_SPLIT 8
+#define ACB_LM_PART_SLOTS 16
 #define ACB_LM_PLAN_BYTES (2u << 20)
 
 typedef struct {
@@ -182,6 +197,8 @@ typedef struct {
     uint64_t seed;     /* Philox key for the on-device sampler */
     int noise_from_buffer; /* 1: take the Exponential(1) noise from acb_lm_buffers.noise / the `noise` argument
                               (parity tests inject torch's stream); 0: on-device Philox */
+    float cfg_coef_beta;   /* double CFG (MusicGen-Style, lm.py:362-376), used when rows == 3*batch = [cond; style-only; null]:
+                              logits = null + cfg_coef * (style + cfg_coef_beta * (cond - style) - null) */
 } acb_lm_sampling;
 
 typedef struct acb_lm acb_lm_t;
@@ -214,7 +231,17 @@ int acb_lm_debug_gemms(acb_lm_t* lm, void* stream, int* n_launches);
 /* 1 if the captured decode step uses programmatic dependent launch edges (ACB_NO_PDL=1 disables them). */
 int acb_lm_uses_pdl(const acb_lm_t* lm);
 
-/* rows the activation buffers must be padded to for `rows` live rows (8, 16, 32 or 64). */
+/* [N][K] row-major fp16 (N % 128 == 0, K % 64 == 0) -> the packed tile layout of acb_lm_weights.wp_*: tile (nt, kb) =
+ * features [128 nt, +128) x K [64 kb, +64) at ((nt * K/64 + kb) * 8192) halves, inside a tile
+ * [16-byte k-chunk (8)][feature (128)][8 halves] (the canonical K-major UMMA layout without swizzle). */
+int acb_lm_pack_weight(const void* w, void* wp, int n, int k, void* stream);
+
+/* Inspection of the fused step's work decomposition: out[4 g + {0,1,2,3}] = N, K, K-splits, 64-element K blocks per item
+ * of GEMM g in {QKV, O, CQ, CO, FF1, FF2, HEADS}; out[28..31] = ring stages, padded rows, phases per step, shared memory
+ * bytes.  Fails when the per-phase path is active. */
+int acb_lm_debug_step_plan(const acb_lm_t* lm, int* out);
+
+/* rows the activation buffers must be padded to for `rows` live rows (16, 32 or 64). */
 int acb_lm_rows_pad(int rows);
 
 /* Number of kernel launches one decode step enqueues (bench.py reports gpu_launches from it). */

@@ -133,9 +133,23 @@ def sin_embedding(positions: torch.Tensor, dim: int, max_period: float = 10000.0
     return torch.cat([torch.cos(phase), torch.sin(phase)], dim=-1)
 
 
+def rope_rotate(x: torch.Tensor, start: int, max_period: float, scale: float) -> torch.Tensor:
+    """RotaryEmbedding.rotate (audiocraft/modules/rope.py:68-69, 75-103): x [R,H,T,hd]; the head dim is hd/2 complex
+    pairs (2i, 2i+1) rotated by (start + t) / max_period^(2i/hd) in fp32, blended with `scale`
+    (rotation * scale + (1 - scale)), cast back to the input dtype."""
+    hd, T = x.shape[-1], x.shape[2]
+    adim = torch.arange(0, hd, 2, dtype=torch.float32)[: hd // 2]
+    freq = 1.0 / (max_period ** (adim / hd))
+    ang = torch.outer(torch.arange(start, start + T, dtype=torch.float32), freq)          # [T, hd/2]
+    rot = torch.polar(torch.ones_like(ang), ang) * scale + (1.0 - scale)
+    xc = torch.view_as_complex(x.float().reshape(*x.shape[:-1], -1, 2).contiguous())
+    return torch.view_as_real(xc * rot.view(1, 1, T, -1)).reshape(x.shape).to(x.dtype)
+
+
 class LMOracle:
     def __init__(self, state_dict: dict, cfg: dict, half_gemm: bool = False):
         self.cfg = cfg
+        self.pos_emb = cfg.get('positional_embedding', 'sin')   # 'sin' | 'rope' | 'sin_rope' (transformer.py:632-637)
         self.half = half_gemm
         self.d = cfg['dim']
         self.H = cfg['num_heads']
@@ -190,6 +204,11 @@ class LMOracle:
         proj = self._q(self._lin(x, self.sd[p + 'in_proj_weight']))
         q, k, v = [self._heads(t) for t in proj.split(self.d, dim=-1)]
         past = 0 if self.kcache[li] is None else self.kcache[li].shape[2]
+        if self.pos_emb in ('rope', 'sin_rope'):
+            # transformer.py:394-395 -> rope.py:106-125: q and the new k rotated at their absolute positions (the number of
+            # cached keys), in fp32, cast back to the fp16 the projections are in under autocast
+            q = self._q(rope_rotate(q, past, self.cfg['max_period'], self.cfg['positional_scale']))
+            k = self._q(rope_rotate(k, past, self.cfg['max_period'], self.cfg['positional_scale']))
         if past:
             k = torch.cat([self.kcache[li], k], dim=2)
             v = torch.cat([self.vcache[li], v], dim=2)
@@ -217,7 +236,8 @@ class LMOracle:
         R, K, S = tokens.shape
         x = sum(F.embedding(tokens[:, k], self.sd[f'emb.{k}.weight']) for k in range(K))  # [R,S,d]
         pos = (torch.arange(S).view(1, -1, 1) + self.offset)
-        x = x + self.cfg['positional_scale'] * sin_embedding(pos, self.d, self.cfg['max_period'])
+        if self.pos_emb in ('sin', 'sin_rope'):   # transformer.py:701-705
+            x = x + self.cfg['positional_scale'] * sin_embedding(pos, self.d, self.cfg['max_period'])
         for li in range(self.L):
             p = f'transformer.layers.{li}.'
             x = x + self._self_attn(li, self._ln(x, p + 'norm1'))
@@ -231,11 +251,16 @@ class LMOracle:
 
     # -- generation
     def next_token(self, seq, cross_cfg, use_sampling, temp, top_k, top_p, cfg_coef, generator, noise,
-                   return_logits=False):
+                   return_logits=False, cfg_coef_beta=None):
         """LMModel._sample_next_token, batched-CFG branch (audiocraft/models/lm.py:390-418): rows doubled
         [cond; uncond], logits = uncond + (cond - uncond) * coef, last step only."""
         B = seq.shape[0]
-        if cross_cfg is not None:
+        if cross_cfg is not None and cfg_coef_beta is not None:
+            # double CFG (lm.py:362-376): rows [cond; style-only; null]
+            all_logits = self.forward(torch.cat([seq, seq, seq], dim=0), cross_cfg)
+            cond, wav, uncond = all_logits.split(B, dim=0)
+            logits = uncond + cfg_coef * (wav + cfg_coef_beta * (cond - wav) - uncond)
+        elif cross_cfg is not None:
             all_logits = self.forward(torch.cat([seq, seq], dim=0), cross_cfg)
             cond, uncond = all_logits.split(B, dim=0)
             logits = uncond + (cond - uncond) * cfg_coef

@@ -5,7 +5,7 @@ Nothing here re-implements the reference: the constructors below are the referen
 (audiocraft/models/encodec.py:125-183 EncodecModel, audiocraft/modules/seanet.py:63,156, audiocraft/quantization/vq.py:16,
 audiocraft/models/lm.py:96-175 LMModel) called with the hyper-parameters of its config tree (restated in
 audiocraft_b200/synth.py).  On CUDA the LM is built the way audiocraft/models/loaders.py:115-118 + builders.py:136-175 do
-it: dtype float16 for the transformer / embeddings / heads, the condition provider left in fp32, and generation runs under
+it: dtype float16 for the transformer only (embeddings, heads and the condition provider stay fp32), and generation runs under
 ``torch.autocast('cuda', float16)`` like audiocraft/models/genmodel.py:74-78.
 """
 import typing as tp
@@ -66,7 +66,7 @@ def build_ref_lm(cfg: dict, sd: tp.Dict[str, torch.Tensor], table: tp.Dict[str, 
     cp_prefix = 'condition_provider.'
     body = {k: v for k, v in sd.items() if not k.startswith(cp_prefix)}
     missing, unexpected = m.load_state_dict(body, strict=False)
-    assert not unexpected and all(k.startswith(cp_prefix) for k in missing), (missing, unexpected)
+    assert not unexpected and all(k.startswith(cp_prefix) or k.endswith('rope.frequencies') for k in missing), (missing, unexpected)
     m.condition_provider.load_state_dict({k[len(cp_prefix):]: v.float() for k, v in sd.items() if k.startswith(cp_prefix)})
     return m.eval(), cond.ConditioningAttributes
 

@@ -212,8 +212,63 @@ def golden_encodec_fullsize():
     print('encodec_32k 2 x 10 s', tuple(codes.shape))
 
 
+def golden_lm_rope():
+    """Rotary positions (modules/rope.py:84-125, transformer.py:394-395, 632-637): lm_mini with positional_embedding
+    'rope' and 'sin_rope' (positional_scale 0.75 so the scale blend is exercised).  Teacher-forced CFG-mixed logits from
+    ONE non-streaming causal forward, and greedy generation in streaming mode with the reference's custom attention
+    (memory_efficient=False) -- the mode tests/modules/test_rope.py:66-90 checks.  (With memory_efficient=True and the
+    'torch' backend the reference's _apply_rope reads past_keys.shape[1], which is the HEAD count in the `b h t d` layout,
+    transformer.py:304-305: streaming then rotates at the wrong offset; that quirk is not reproduced.)"""
+    out = {}
+    for pe in ('rope', 'sin_rope'):
+        cfg = synth.lm_config('lm_mini')
+        cfg['positional_embedding'], cfg['positional_scale'] = pe, 0.75
+        sd = synth.synth_lm_state_dict(cfg, seed=3)
+        B, t_text, T = 2, 5, 12
+        hid, mask, cross = H.lm_condition(cfg, sd, B, t_text, 1)
+        table = {f'd{i}': (hid[i], mask[i]) for i in range(B)}
+        table['__null__'] = (torch.zeros(t_text, cfg['cond_dim']), torch.zeros(t_text, dtype=torch.long))
+        m, CA = _build_ref_lm(cfg, sd, table, positional_embedding=pe, positional_scale=0.75, memory_efficient=False, custom=True)
+        seq = H.fullsize_sequence(cfg, B, T, 5)
+        ct = {'description': (cross, torch.ones(cross.shape[:2], dtype=torch.long))}
+        lg = m(torch.cat([seq, seq], 0)[..., :-1], conditions=[], condition_tensors=ct)
+        c, u = lg.split(B, dim=0)
+        conds = [CA(text={'description': f'd{i}'}) for i in range(B)]
+        out[pe] = dict(logits=(u + (c - u) * cfg['cfg_coef']).permute(2, 0, 1, 3).contiguous(),   # [S-1, B, K, card]
+                       greedy=m.generate(None, conds, max_gen_len=T, use_sampling=False))
+    out.update(batch=2, t_text=5, T=12, wseed=3, cseed=1, sseed=5, positional_scale=0.75)
+    torch.save(out, os.path.join(H.GOLDEN_DIR, 'lm_mini_rope.pt'))
+    print('lm_mini_rope ok')
+
+
+def golden_two_step():
+    """LMModel.generate(two_step_cfg=True) (lm.py:376-391, 497-503): two separate passes per step with their own streaming
+    states, and the quirk that this branch mixes with self.cfg_coef, not the `cfg_coef` argument (lm.py:387)."""
+    cfg = synth.lm_config('lm_mini')
+    sd = synth.synth_lm_state_dict(cfg, seed=3)
+    B, t_text, T = 2, 5, 12
+    hid, mask, _ = H.lm_condition(cfg, sd, B, t_text, 1)
+    table = {f'd{i}': (hid[i], mask[i]) for i in range(B)}
+    table['__null__'] = (torch.zeros(t_text, cfg['cond_dim']), torch.zeros(t_text, dtype=torch.long))
+    m, CA = _build_ref_lm(cfg, sd, table)
+    conds = [CA(text={'description': f'd{i}'}) for i in range(B)]
+    out = dict(batch=B, t_text=t_text, T=T, wseed=3, cseed=1,
+               two_step=m.generate(None, conds, max_gen_len=T, use_sampling=False, two_step_cfg=True, cfg_coef=1.5),
+               batched_coef_1p5=m.generate(None, conds, max_gen_len=T, use_sampling=False, two_step_cfg=False, cfg_coef=1.5),
+               batched_default=m.generate(None, conds, max_gen_len=T, use_sampling=False))
+    assert torch.equal(out['two_step'], out['batched_default'])   # the quirk: two-step ignores cfg_coef=1.5
+    torch.save(out, os.path.join(H.GOLDEN_DIR, 'lm_mini_two_step.pt'))
+    print('two_step ok; differs from coef 1.5:', not torch.equal(out['two_step'], out['batched_coef_1p5']))
+
+
 if __name__ == '__main__':
     os.makedirs(H.GOLDEN_DIR, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'two_step':
+        golden_two_step()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'rope':
+        golden_lm_rope()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'fullsize':
         golden_encodec_fullsize()
         golden_lm_fullsize('musicgen_medium', 8)
@@ -229,3 +284,5 @@ if __name__ == '__main__':
     golden_lm('lm_tiny', 3, 4, 9, 4, 2, steps_logits=12)
     golden_lm('musicgen_small', 1, 6, 3, 9, 5, steps_logits=6, topn=32)
     golden_stereo()
+    golden_lm_rope()
+    golden_two_step()

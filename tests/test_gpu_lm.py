@@ -344,3 +344,99 @@ def test_audiogen_api():
     wav, tok = ag.generate(['dog barking', 'rain'], return_tokens=True)
     assert tok.shape == (2, 4, 50) and wav.shape == (2, 1, 16000)
     assert 'cfg_coef_beta' not in ag.generation_params
+
+
+@pytest.mark.parametrize('pe', ['rope', 'sin_rope'])
+def test_rope_matches_oracle_and_reference_golden(pe):
+    """Rotary positions in the fused step's QKV -> cache path (rope.py:84-125 at transformer.py:394-395): teacher-forced
+    logits vs the fp16-emulating oracle (2e-2) and the fp32 reference golden (6e-2), greedy tokens vs the reference."""
+    g = _golden('lm_mini_rope')
+    cfg = synth.lm_config('lm_mini')
+    cfg['positional_embedding'], cfg['positional_scale'] = pe, g['positional_scale']
+    sd = synth.synth_lm_state_dict(cfg, seed=g['wseed'])
+    from audiocraft_b200.lm import LMModel
+    m = LMModel(sd, cfg, None, None, 'cuda')
+    B, T = g['batch'], g['T']
+    _, _, cross = H.lm_condition(cfg, sd, B, g['t_text'], g['cseed'])
+    seq = H.fullsize_sequence(cfg, B, T, g['sseed'])
+    lg = m.teacher_forced_logits(seq, cross, cfg['cfg_coef']).cpu()
+    o = LO.LMOracle(sd, cfg, half_gemm=True)
+    o.reset()
+    outs = [o.forward(torch.cat([seq, seq], 0)[..., t:t + 1], cross) for t in range(seq.shape[-1] - 1)]
+    c, u = torch.cat(outs, dim=2).split(B, dim=0)
+    want = (u + (c - u) * cfg['cfg_coef']).permute(2, 0, 1, 3)
+    print(f'{pe}: max |logit diff| vs oracle {(lg - want).abs().max():.3e}, vs fp32 reference {(lg - g[pe]["logits"]).abs().max():.3e}')
+    torch.testing.assert_close(lg, want, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(lg, g[pe]['logits'], rtol=6e-2, atol=6e-2)
+    out = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross)
+    assert torch.equal(out.cpu(), g[pe]['greedy'])
+
+
+def test_two_step_cfg_matches_reference_golden():
+    """two_step_cfg=True (lm.py:376-391): the reference runs the conditional and the null pass separately with their own
+    streaming states and mixes with self.cfg_coef (NOT the cfg_coef argument, lm.py:387).  Rows are independent in every
+    kernel, so one batched pass is the same arithmetic; the golden tokens come from the reference's literal two-step run."""
+    g = _golden('lm_mini_two_step')
+    cfg, sd, m = _model('lm_mini', g['wseed'])
+    B, T = g['batch'], g['T']
+    _, _, cross = H.lm_condition(cfg, sd, B, g['t_text'], g['cseed'])
+    out = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross,
+                     two_step_cfg=True, cfg_coef=1.5).cpu()
+    assert torch.equal(out, g['two_step'])
+    out = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross, cfg_coef=1.5).cpu()
+    assert torch.equal(out, g['batched_coef_1p5'])
+
+
+def test_streaming_state_roundtrip_and_literal_two_step():
+    """StreamingModule surface (streaming.py:59-119): get/set_streaming_state restore the decode exactly, the state has
+    the reference's keys and shapes ([rows, H, t, 64], offsets [rows]), and a LITERAL two-step CFG -- conditional rows and
+    null rows decoded in separate streaming sessions, mixed on the host -- equals the batched pass."""
+    cfg, sd, m = _model('lm_mini', 3)
+    B, K, card = 2, cfg['n_q'], cfg['card']
+    _, _, cross = H.lm_condition(cfg, sd, B, 5, 1)
+    gen = torch.Generator().manual_seed(9)
+    toks = torch.randint(0, card, (8, B, K), generator=gen)
+    m.streaming_begin(B, cross, max_len=16)
+    first = [m.streaming_step(toks[i]) for i in range(5)]
+    state = m.get_streaming_state()
+    assert state['transformer.offsets'].tolist() == [5] * (2 * B)
+    assert state['transformer.layers.0.self_attn.past_keys'].shape == (2 * B, cfg['num_heads'], 5, 64)
+    a = [m.streaming_step(toks[i]).clone() for i in range(5, 8)]
+    m.set_streaming_state(state)
+    b = [m.streaming_step(toks[i]).clone() for i in range(5, 8)]
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    # literal two-step: cond rows only, then null rows only (coef 1 => the session returns its rows' raw logits)
+    m.streaming_begin(B, cross[:B], max_len=16, cfg_coef=1.0)
+    lc = [m.streaming_step(toks[i]).clone() for i in range(5)]
+    m.streaming_begin(B, cross[B:], max_len=16, cfg_coef=1.0)
+    lu = [m.streaming_step(toks[i]).clone() for i in range(5)]
+    for i in range(5):
+        mixed = lu[i] + (lc[i] - lu[i]) * cfg['cfg_coef']
+        torch.testing.assert_close(mixed, first[i], rtol=0, atol=1e-5)
+    m.reset_streaming()
+    assert int(m._bufs['pos'][0]) == 0
+
+
+def test_double_cfg_matches_oracle():
+    """cfg_coef_beta (MusicGen-Style double CFG, lm.py:362-376) with [cond; style-only; null] rows."""
+    cfg, sd, m = _model('lm_mini', 3)
+    B, T = 2, 8
+    _, _, cross2 = H.lm_condition(cfg, sd, B, 5, 1)
+    _, _, other = H.lm_condition(cfg, sd, B, 5, 4)
+    cross3 = torch.cat([cross2[:B], other[:B] * 0.5, cross2[B:]], 0)      # a stand-in "style-only" condition in the middle
+    o = LO.LMOracle(sd, cfg, half_gemm=True)
+    K, special = cfg['n_q'], cfg['card']
+    seq = torch.full((B, K, 1), special, dtype=torch.long)
+    o.reset()
+    want = []
+    cur = seq
+    m.streaming_begin(B, cross3, max_len=T + 4, cfg_coef=2.0, cfg_coef_beta=3.0)
+    for i in range(6):
+        tok, lg = o.next_token(cur, cross3, False, 1.0, 0, 0.0, 2.0, None, None, return_logits=True, cfg_coef_beta=3.0)
+        got = m.streaming_step(cur[..., 0]).cpu()
+        print(f'step {i}: double-CFG logits max diff vs oracle {(got - lg).abs().max():.3e}')
+        torch.testing.assert_close(got, lg, rtol=3e-2, atol=3e-2)
+        cur = tok
+    with pytest.raises(AssertionError):
+        m.generate(None, [], num_samples=B, max_gen_len=T, cross_attention_src=cross3)   # 3B rows need cfg_coef_beta

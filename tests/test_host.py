@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert L.acb_version() >= 100
-    assert L.acb_lm_rows_pad(1) == 8 and L.acb_lm_rows_pad(16) == 16 and L.acb_lm_rows_pad(17) == 32
+    assert L.acb_lm_rows_pad(1) == 16 and L.acb_lm_rows_pad(16) == 16 and L.acb_lm_rows_pad(17) == 32 and L.acb_lm_rows_pad(64) == 64
     assert L.acb_lstm_state_bytes(2, 8) == (2 * 2 * 8 + 64) * 4
 
 

@@ -161,3 +161,44 @@ def test_oracle_matches_huggingface_encodec(shortcut):
     codes, scale = o.encode(x)
     assert scale is None and torch.equal(codes, enc[0][0])
     torch.testing.assert_close(o.decode(codes), dec, rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize('pe', ['rope', 'sin_rope'])
+def test_lm_oracle_rope_matches_reference(pe):
+    """Rotary positions (rope.py:84-125): teacher-forced logits of one causal forward and streaming greedy tokens."""
+    g = _load('lm_mini_rope.pt')
+    cfg = synth.lm_config('lm_mini')
+    cfg['positional_embedding'], cfg['positional_scale'] = pe, g['positional_scale']
+    sd = synth.synth_lm_state_dict(cfg, seed=g['wseed'])
+    B, T = g['batch'], g['T']
+    _, _, cross = H.lm_condition(cfg, sd, B, g['t_text'], g['cseed'])
+    seq = H.fullsize_sequence(cfg, B, T, g['sseed'])
+    o = LO.LMOracle(sd, cfg)
+    o.reset()
+    outs = [o.forward(torch.cat([seq, seq], 0)[..., t:t + 1], cross) for t in range(seq.shape[-1] - 1)]   # streaming
+    lg = torch.cat(outs, dim=2)
+    c, u = lg.split(B, dim=0)
+    mixed = (u + (c - u) * cfg['cfg_coef']).permute(2, 0, 1, 3)
+    torch.testing.assert_close(mixed, g[pe]['logits'], rtol=0, atol=5e-5)
+    assert torch.equal(o.generate(None, cross, B, T, use_sampling=False), g[pe]['greedy'])
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize('name', ['musicgen_medium', 'musicgen_large'])
+def test_lm_oracle_fulldepth_matches_reference(name):
+    """Full-depth released architectures over 1500 frames (tests/golden/*_full.pt): minutes of CPU per model, so only
+    with ACB_SLOW_TESTS=1 (the GPU suite checks the CUDA path against the same fixtures, tests/test_gpu_fullsize.py)."""
+    import os as _os
+    if _os.environ.get('ACB_SLOW_TESTS') != '1':
+        pytest.skip('set ACB_SLOW_TESTS=1 (about 10 CPU-minutes per model)')
+    g = _load(f'{name}_full.pt')
+    cfg = synth.lm_config(name)
+    sd = synth.synth_lm_state_dict(cfg, seed=g['wseed'])
+    B = g['batch']
+    _, _, cross = H.lm_condition(cfg, sd, B, g['t_text'], g['cseed'])
+    seq = H.fullsize_sequence(cfg, B, g['T'], g['sseed'])
+    o = LO.LMOracle(sd, cfg)
+    lg = o.forward(torch.cat([seq, seq], 0)[..., :-1], cross)
+    c, u = lg.split(B, dim=0)
+    mixed = (u + (c - u) * cfg['cfg_coef'])[:, :, g['steps'], :].permute(2, 0, 1, 3)
+    torch.testing.assert_close(mixed.gather(-1, g['logits_top_i'].long()), g['logits_top_v'], rtol=0, atol=2e-4)
