@@ -18,6 +18,8 @@ HEADERS = ['common.cuh', 'gridbar.cuh', 'lm_step.cuh', os.path.join('..', '..', 
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC',
          '-Xptxas', '-v']
+if os.environ.get('ACB_STEP_NCW'):   # experiment: compute warps per CTA of the fused decode step (csrc/lm_step.cu)
+    FLAGS.append('-DACB_STEP_NCW=' + os.environ['ACB_STEP_NCW'])
 if os.environ.get('ACB_BUILD_TIMELINE') == '1':   # instrumented build: in-kernel %globaltimer stamps (see csrc/lm.cu tl_stamp)
     FLAGS.append('-DACB_TIMELINE')
 

@@ -105,7 +105,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict__ emb, const float* __restrict__ inv_freq,
                                                        const int64_t* __restrict__ seq, const int* __restrict__ P,
                                                        float* __restrict__ x, int d, int n_q, int card, int max_seq,
-                                                       int batch, float pos_scale, float* __restrict__ stats) {
+                                                       int batch, float pos_scale) {
     pdl_trigger();
     pdl_wait();
     const int r = blockIdx.x, b = r % batch, pos = P[0];
@@ -123,11 +123,6 @@ __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict_
         const float phase = (float)pos / inv_freq[j];
         v += pos_scale * (i < half_d ? cosf(phase) : sinf(phase));
         x[(size_t)r * d + i] = v;
-        if (stats) {   // per 32-feature tile: (sum, centred sum of squares) for the LayerNorm of the first consumer
-            const float sm = warp_sum(v), dv = v - sm * (1.f / 32.f), m2 = warp_sum(dv * dv);
-            if ((threadIdx.x & 31) == 0)
-                *reinterpret_cast<float2*>(stats + ((size_t)(i >> 5) * gridDim.x + r) * 2) = make_float2(sm, m2);
-        }
     }
 }
 
@@ -137,7 +132,6 @@ __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict_
 // time scale cold instruction fetch is a first-order cost (the 4-float4-per-thread version was 1 048 instructions and
 // spent 1-2 us before its first load was consumed).  gamma / beta do not depend on the previous kernel and are
 // requested before griddepcontrol.wait.
-constexpr int LN_MAX_PER_THREAD = 16;   // kept for the dim bound check in acb_lm_create
 constexpr int LN_THREADS = 512;
 __global__ void __launch_bounds__(LN_THREADS) lm_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int nsplit,
                                                            size_t split_stride, const float* __restrict__ gamma,
@@ -321,332 +315,6 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
         }
     }
     tl_stamp(p.timing, 3);
-}
-
-// ------------------------------------------------------------------------------------------------ wide skinny GEMM
-// Second-generation decode GEMM ("v6", opt-in with ACB_LM_STEP=v6: parity-tested, but measured SLOWER than the default
-// step -- 2.55 vs 2.25 ms at KV 1, see DESIGN.md section 3.1 for the in-kernel time stamps).  What it changes and why:
-//   * activations are the A operand (16 rows = one m16 tile), weights the B operand, so a CTA owns 8*FG output features
-//     (FG = 4: 32) and every activation fragment a warp loads is reused for FG feature groups: activation traffic out
-//     of L2 is 16/(8*FG) of the weight bytes instead of equal to them (the 16-feature tile re-read the activations once
-//     per tile: measured L2->SM traffic was 2x the HBM traffic, and the LTS cap is only ~2x HBM bandwidth).
-//   * split-K partial sums never go to global memory: the K-slices of one feature tile form a thread-block CLUSTER, the
-//     non-leader CTAs push their 16 x 32 partial tile into the leader's shared memory (st.shared::cluster), one cluster
-//     barrier, and the leader reduces in a fixed order (bit-reproducible) and runs the epilogue.
-//   * the residual add and LayerNorm are folded into the GEMMs on either side: a producer (WEPI_RESID) writes
-//     x += y and per-(tile,row) statistics (sum, centred sum of squares); a consumer (LNIN) merges those 48 tile
-//     statistics per row (Chan's formula: no E[x^2]-mean^2 cancellation) and normalises the fp32 residual stream while
-//     loading its A fragments.  The three LayerNorm kernels per layer disappear: 8 dependent kernels per layer, not 11.
-enum { WEPI_RESID = 0, WEPI_QKV = 1, WEPI_GELU = 2, WEPI_F32 = 3 };
-
-struct WGemmParams {
-    const __half* W;           // [N][K] fp16, reference layout
-    const __half* X16;         // !LNIN: A operand [>= rows][K] fp16
-    const float* X32;          // LNIN: residual stream [rows][K] fp32 (K == model dim), normalised on load
-    const float* gamma; const float* beta; const float* stats_in; int stat_tiles; float stat_w, inv_stat_w, inv_k;
-    int N, K, rows, kslice, nsplit;
-    float* x; float* stats_out;                                                  // RESID (ld = N)
-    float* out_f32; int ld_out;                                                  // F32
-    __half* out_f16;                                                             // GELU (ld = ld_out)
-    float* q32; __half* kc; __half* vc; int d, H, cache_len; const int* pos;     // QKV
-    unsigned long long* timing;   // debug (ACB_LM_TIMING=1): per CTA, 8 time stamps of thread 0
-};
-
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
-__device__ __forceinline__ void st_cluster_f32(uint32_t local_smem_addr, uint32_t cta_rank, float v) {
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(cta_rank));
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
-}
-#ifdef ACB_TIMELINE
-__device__ __forceinline__ void wg_stamp(const WGemmParams& p, int slot) {
-    if (p.timing && threadIdx.x == 0) {
-        unsigned long long t;
-        if (slot == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        else t = (unsigned long long)clock64();
-        p.timing[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
-    }
-}
-#else
-__device__ __forceinline__ void wg_stamp(const WGemmParams&, int) {}
-#endif
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// shared-memory layout, shared by the kernel and the host-side size computation
-constexpr int WG_WARPS = 8, WG_THREADS = WG_WARPS * 32, WG_MAX_STAT = 8;   // statistics tiles per lane: d <= 2048
-struct WSmem { int pitch_w, bar, gb, mr, red, recv, total; };
-__host__ __device__ inline WSmem wgemm_smem(int MT, int FG, bool lnin, int kslice, int nsplit) {
-    const int R = 16 * MT, FT = 8 * FG;
-    WSmem L;
-    L.pitch_w = kslice * 2 + 64;                       // = 64 mod 128 when kslice % 64 == 0: conflict-free 128-bit reads
-    L.bar = FT * L.pitch_w;
-    L.gb = L.bar + 16;                                 // gamma[kslice], beta[kslice]
-    L.mr = L.gb + (lnin ? kslice * 8 : 0);             // (mean, rstd) per row
-    L.red = L.mr + (lnin ? R * 8 : 0);                 // [warps][R][FT + 1]
-    L.recv = L.red + WG_WARPS * R * (FT + 1) * 4;      // [nsplit - 1][R][FT]: partial tiles pushed by the other K-slices
-    L.total = L.recv + (nsplit - 1) * R * FT * 4;
-    return L;
-}
-
-// One k-block (32 reduction indices) of the A operand as this lane holds it: rows g and g+8 of every 16-row tile,
-// 8 consecutive k each -- raw fp32 residual values (normalised when consumed) or fp16 activations.
-template <int MT, bool LNIN> struct WFrag;
-template <int MT> struct WFrag<MT, true> { float4 a[MT][2], b[MT][2]; };
-template <int MT> struct WFrag<MT, false> { uint4 a[MT], b[MT]; };
-
-// The lane's row pointers (rows g and g+8 of every tile, at its first k); null for rows that do not exist.
-template <int MT> struct WRows { const unsigned char* a[MT]; const unsigned char* b[MT]; };
-
-template <int MT, bool LNIN>
-__device__ __forceinline__ void wfrag_load(WFrag<MT, LNIN>& f, const WRows<MT>& rp, int byte_off) {
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-        if constexpr (LNIN) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            f.a[mt][0] = rp.a[mt] ? *reinterpret_cast<const float4*>(rp.a[mt] + byte_off) : z;
-            f.a[mt][1] = rp.a[mt] ? *reinterpret_cast<const float4*>(rp.a[mt] + byte_off + 16) : z;
-            f.b[mt][0] = rp.b[mt] ? *reinterpret_cast<const float4*>(rp.b[mt] + byte_off) : z;
-            f.b[mt][1] = rp.b[mt] ? *reinterpret_cast<const float4*>(rp.b[mt] + byte_off + 16) : z;
-        } else {
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            f.a[mt] = rp.a[mt] ? *reinterpret_cast<const uint4*>(rp.a[mt] + byte_off) : z;
-            f.b[mt] = rp.b[mt] ? *reinterpret_cast<const uint4*>(rp.b[mt] + byte_off) : z;
-        }
-    }
-}
-
-// Code size matters here: a decode GEMM runs for ~3 us, and every instruction line is fetched once per launch like
-// data (the first version of this kernel, with the LayerNorm arithmetic unrolled over four k-blocks in flight, was
-// 2 760 instructions = 44 KB and took ~5 us longer per launch than the 430-instruction round-1 kernel).  So the k-loop
-// is ONE compact body (`#pragma unroll 1`), software-pipelined by hand: the next k-block's activations are requested
-// before the current one is normalised and multiplied; 8 warps split the K-slice so each runs only 2-3 iterations.
-template <int MT, int FG, bool LNIN, int EPI>
-__global__ void __launch_bounds__(WG_THREADS) lm_wgemm_kernel(WGemmParams p) {
-    constexpr int R = 16 * MT, FT = 8 * FG, RP = FT + 1;
-    static_assert(EPI != WEPI_RESID || FG == 4, "the residual epilogue needs a 32-feature tile (one warp per row)");
-    extern __shared__ __align__(128) unsigned char gsm[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c4 = lane & 3;
-    const int f0 = blockIdx.x * FT;
-    const uint32_t rank = cluster_ctarank();         // == blockIdx.y: the grid is (tiles, nsplit), the cluster (1, nsplit, 1)
-    const int ks = p.kslice, k0 = (int)blockIdx.y * ks;   // K % (32 * nsplit) == 0: every slice is full
-    const WSmem L = wgemm_smem(MT, FG, LNIN, ks, p.nsplit);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + L.bar);
-    float* gbs = reinterpret_cast<float*>(gsm + L.gb);
-    float* mr = reinterpret_cast<float*>(gsm + L.mr);
-    float* red = reinterpret_cast<float*>(gsm + L.red);
-    float* recv = reinterpret_cast<float*>(gsm + L.recv);
-
-    wg_stamp(p, 0); wg_stamp(p, 1);
-    // ---- prologue that does not depend on the previous kernel: weight slab (TMA), gamma/beta
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (p.nsplit > 1) cluster_arrive();              // "this CTA runs": its shared memory may be written by its peers
-    if (warp == 0) {
-        const int nfeat = min(FT, p.N - f0);
-        if (lane == 0) mbar_expect_tx(bar, (uint32_t)nfeat * (uint32_t)ks * 2u);
-        __syncwarp();
-        if (lane < nfeat) bulk_g2s(gsm + lane * L.pitch_w, p.W + (size_t)(f0 + lane) * p.K + k0, (uint32_t)ks * 2u, bar);
-    }
-    if constexpr (LNIN) {
-#pragma unroll 1
-        for (int i = tid; i < (ks >> 2); i += WG_THREADS) {
-            reinterpret_cast<float4*>(gbs)[i] = reinterpret_cast<const float4*>(p.gamma + k0)[i];
-            reinterpret_cast<float4*>(gbs + ks)[i] = reinterpret_cast<const float4*>(p.beta + k0)[i];
-        }
-    }
-    pdl_trigger();
-    pdl_wait();   // x / activations / statistics written by the previous kernels are visible from here on
-    wg_stamp(p, 2);
-
-    // warp w reduces over k-blocks [kb0, kb1) of the slice; its first activations are requested before anything else
-    const int nkb = ks >> 5;
-    const int kbw = (nkb + WG_WARPS - 1) / WG_WARPS;
-    const int kb0 = min(nkb, warp * kbw), kb1 = min(nkb, kb0 + kbw);
-    constexpr int ESZ = LNIN ? 4 : 2;                // bytes per activation element
-    WRows<MT> rp;
-    {
-        const unsigned char* xbase = LNIN ? reinterpret_cast<const unsigned char*>(p.X32) : reinterpret_cast<const unsigned char*>(p.X16);
-        xbase += ((size_t)g * p.K + k0 + 8 * c4) * ESZ;
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            rp.a[mt] = 16 * mt + g < p.rows ? xbase + (size_t)(16 * mt) * p.K * ESZ : nullptr;
-            rp.b[mt] = 16 * mt + g + 8 < p.rows ? xbase + (size_t)(16 * mt + 8) * p.K * ESZ : nullptr;
-        }
-    }
-    WFrag<MT, LNIN> cur, nxt;
-    if (kb0 < kb1) wfrag_load<MT, LNIN>(cur, rp, kb0 * 32 * ESZ);
-
-    // ---- LayerNorm statistics of every row from the producer's per-tile (sum, M2): 8 lanes per row, one pass
-    if constexpr (LNIN) {
-        const int sub = tid & 7;
-        const float inv_k = p.inv_k, inv_w = p.inv_stat_w;
-#pragma unroll 1
-        for (int row = tid >> 3; row < R; row += WG_THREADS / 8) {   // warp-uniform trip count
-            const float2* st = reinterpret_cast<const float2*>(p.stats_in) + row;
-            float2 sv[WG_MAX_STAT];
-            float sm = 0.f;
-#pragma unroll
-            for (int i = 0; i < WG_MAX_STAT; ++i) {
-                const int t = sub + 8 * i;
-                sv[i] = (row < p.rows && t < p.stat_tiles) ? st[(size_t)t * p.rows] : make_float2(0.f, 0.f);
-                sm += sv[i].x;
-            }
-            sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-            sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-            sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-            const float mean = sm * inv_k;
-            float m2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < WG_MAX_STAT; ++i) {
-                const float dm = sv[i].x * inv_w - mean;
-                if (sub + 8 * i < p.stat_tiles) m2 += sv[i].y + p.stat_w * dm * dm;
-            }
-            m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
-            m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
-            m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
-            if (sub == 0) { mr[row * 2] = mean; mr[row * 2 + 1] = rsqrtf(m2 * inv_k + 1e-5f); }
-        }
-        __syncthreads();   // mr and the gamma/beta staging
-    }
-    float mean_a[MT], rstd_a[MT], mean_b[MT], rstd_b[MT];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-        if constexpr (LNIN) {
-            mean_a[mt] = mr[(16 * mt + g) * 2]; rstd_a[mt] = mr[(16 * mt + g) * 2 + 1];
-            mean_b[mt] = mr[(16 * mt + g + 8) * 2]; rstd_b[mt] = mr[(16 * mt + g + 8) * 2 + 1];
-        } else {
-            mean_a[mt] = rstd_a[mt] = mean_b[mt] = rstd_b[mt] = 0.f;
-        }
-    }
-
-    float c[MT][FG][4];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int fg = 0; fg < FG; ++fg) c[mt][fg][0] = c[mt][fg][1] = c[mt][fg][2] = c[mt][fg][3] = 0.f;
-
-    wg_stamp(p, 3);
-    mbar_wait(bar, 0);   // the weight slab has landed (every thread waits: never leave with a bulk copy in flight)
-    wg_stamp(p, 4);
-    const unsigned char* wrow = gsm + g * L.pitch_w + 16 * c4;
-#pragma unroll 1
-    for (int kb = kb0; kb < kb1; ++kb) {
-        if (kb + 1 < kb1) wfrag_load<MT, LNIN>(nxt, rp, (kb + 1) * 32 * ESZ);
-        uint4 qa[MT], qb[MT];
-        if constexpr (LNIN) {
-            const int kl = kb * 32 + 8 * c4;   // first of this lane's 8 consecutive k inside the slice
-            const float4 g0 = *reinterpret_cast<const float4*>(gbs + kl), g1 = *reinterpret_cast<const float4*>(gbs + kl + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(gbs + ks + kl), b1 = *reinterpret_cast<const float4*>(gbs + ks + kl + 4);
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const float4 a0 = cur.a[mt][0], a1 = cur.a[mt][1], e0 = cur.b[mt][0], e1 = cur.b[mt][1];
-                const float ma = mean_a[mt], sa = rstd_a[mt], mb = mean_b[mt], sb = rstd_b[mt];
-                qa[mt].x = pack_h2((a0.x - ma) * sa * g0.x + b0.x, (a0.y - ma) * sa * g0.y + b0.y);
-                qa[mt].y = pack_h2((a0.z - ma) * sa * g0.z + b0.z, (a0.w - ma) * sa * g0.w + b0.w);
-                qa[mt].z = pack_h2((a1.x - ma) * sa * g1.x + b1.x, (a1.y - ma) * sa * g1.y + b1.y);
-                qa[mt].w = pack_h2((a1.z - ma) * sa * g1.z + b1.z, (a1.w - ma) * sa * g1.w + b1.w);
-                qb[mt].x = pack_h2((e0.x - mb) * sb * g0.x + b0.x, (e0.y - mb) * sb * g0.y + b0.y);
-                qb[mt].y = pack_h2((e0.z - mb) * sb * g0.z + b0.z, (e0.w - mb) * sb * g0.w + b0.w);
-                qb[mt].z = pack_h2((e1.x - mb) * sb * g1.x + b1.x, (e1.y - mb) * sb * g1.y + b1.y);
-                qb[mt].w = pack_h2((e1.z - mb) * sb * g1.z + b1.z, (e1.w - mb) * sb * g1.w + b1.w);
-                // (rows >= p.rows were loaded as zeros and normalise to finite values that only reach output rows the
-                //  epilogue never stores)
-            }
-        } else {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) { qa[mt] = cur.a[mt]; qb[mt] = cur.b[mt]; }
-        }
-#pragma unroll
-        for (int fg = 0; fg < FG; ++fg) {
-            // 8 consecutive k of feature fg*8+g: k-pairs P0..P3; the same k permutation as the A rows
-            const uint4 wv = *reinterpret_cast<const uint4*>(wrow + fg * 8 * L.pitch_w + kb * 64);
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                mma16816(c[mt][fg], qa[mt].x, qb[mt].x, qa[mt].y, qb[mt].y, wv.x, wv.y);
-                mma16816(c[mt][fg], qa[mt].z, qb[mt].z, qa[mt].w, qb[mt].w, wv.z, wv.w);
-            }
-        }
-        cur = nxt;
-    }
-
-    wg_stamp(p, 5);
-    // ---- K reduction: the warps of the CTA (fixed order), then the K-slices of the cluster (fixed order)
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int fg = 0; fg < FG; ++fg) {
-            float* r0 = red + (warp * R + 16 * mt + g) * RP + fg * 8 + 2 * c4;
-            r0[0] = c[mt][fg][0]; r0[1] = c[mt][fg][1];
-            r0[8 * RP] = c[mt][fg][2]; r0[8 * RP + 1] = c[mt][fg][3];
-        }
-    __syncthreads();
-    constexpr int EPT = (R * FT + WG_THREADS - 1) / WG_THREADS;   // tile elements per thread
-    float v[EPT];
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        const int idx = tid + WG_THREADS * j, row = idx / FT, feat = idx % FT;
-        float a = 0.f;
-        if (idx < R * FT)
-#pragma unroll
-            for (int w = 0; w < WG_WARPS; ++w) a += red[(w * R + row) * RP + feat];
-        v[j] = a;
-    }
-    if (p.nsplit > 1) {
-        cluster_wait();                                // every CTA of the cluster has started
-        if (rank != 0) {
-#pragma unroll
-            for (int j = 0; j < EPT; ++j)
-                if (tid + WG_THREADS * j < R * FT)
-                    st_cluster_f32(smem_u32(recv + (rank - 1) * R * FT + tid + WG_THREADS * j), 0u, v[j]);
-        }
-        cluster_sync_all();                            // release the pushes / acquire them in the leader
-        wg_stamp(p, 6);
-        if (rank != 0) return;
-#pragma unroll 1
-        for (int s = 0; s < p.nsplit - 1; ++s)
-#pragma unroll
-            for (int j = 0; j < EPT; ++j)
-                if (tid + WG_THREADS * j < R * FT) v[j] += recv[s * R * FT + tid + WG_THREADS * j];
-    }
-
-    // ---- epilogue (leader CTA of the tile)
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        const int idx = tid + WG_THREADS * j, row = idx / FT, feat = idx % FT, n = f0 + feat;
-        if constexpr (EPI == WEPI_RESID) {
-            // FT == 32: a warp holds the 32 features of one row.  x += y, and the tile's LayerNorm statistics.
-            if (row < p.rows) {   // warp-uniform (R * FT is a multiple of WG_THREADS here)
-                float* xp = p.x + (size_t)row * p.N + n;
-                const float xn = *xp + v[j];
-                *xp = xn;
-                const float sm = warp_sum(xn), dv = xn - sm * (1.f / 32.f), m2 = warp_sum(dv * dv);
-                if (lane == 0)
-                    *reinterpret_cast<float2*>(p.stats_out + ((size_t)blockIdx.x * p.rows + row) * 2) = make_float2(sm, m2);
-            }
-        } else {
-            if (idx >= R * FT || row >= p.rows || n >= p.N) continue;
-            if (EPI == WEPI_F32) {
-                p.out_f32[(size_t)row * p.ld_out + n] = v[j];
-            } else if (EPI == WEPI_GELU) {
-                p.out_f16[(size_t)row * p.ld_out + n] = __float2half_rn(gelu_erf(half_round(v[j])));
-            } else {  // WEPI_QKV: the tile lies inside one of q / k / v and inside one head (FT | 64, d % 64 == 0)
-                const int which = f0 >= 2 * p.d ? 2 : (f0 >= p.d ? 1 : 0), nn = n - which * p.d;
-                if (which == 0) {
-                    p.q32[(size_t)row * p.d + nn] = v[j];
-                } else {
-                    __half* cache = which == 2 ? p.vc : p.kc;
-                    cache[(((size_t)row * p.H + (nn >> 6)) * p.cache_len + p.pos[0]) * 64 + (nn & 63)] = __float2half_rn(v[j]);
-                }
-            }
-        }
-    }
-    wg_stamp(p, 7);
 }
 
 // ------------------------------------------------------------------------------------------------ attention (1 query)
@@ -1093,224 +761,6 @@ __global__ void __launch_bounds__(1024) lm_sample_kernel(SampleParams p) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------ chain kernel
-// A decode step is a strict dependency chain of ~11 small phases per layer; as separate kernels each phase pays a
-// ~4 us kernel boundary, 4x what its HBM traffic needs.  The chain kernel runs every GEMM / LayerNorm phase that lies
-// between two attention kernels inside ONE persistent kernel: all CTAs are co-resident (2 per SM), phases are
-// separated by a grid barrier (one atomic + an acquire spin, ~1 us), and because a CTA's weight slabs are static it
-// prefetches them with TMA bulk copies TWO GEMM phases ahead, so the HBM weight stream keeps running through
-// barriers and LayerNorm phases.  Activations written by other CTAs of the same launch are read with ld.global.cg
-// (L1 is not coherent across SMs).
-enum { PH_GEMM = 0, PH_LN = 1 };
-struct ChainPhase {
-    int kind;
-    // PH_GEMM
-    const __half* W; const __half* X16; int N, K, kslice, nsplit, epi;
-    float* out_f32; int ld_out; size_t split_stride; __half* out_f16;
-    float* q32; __half* kc; __half* vc; int d, H, cache_len;
-    // PH_LN
-    float* x; const float* part; int ln_nsplit; size_t ln_split_stride; const float* gamma; const float* beta; __half* ln_out;
-};
-struct ChainParams { const ChainPhase* ph; int nph, rows, slab_bytes; unsigned* bar; const int* pos; };
-
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void chain_issue(const ChainPhase& P, int item, unsigned char* buf, uint64_t* bar) {
-    const int tiles = P.N >> 4, f0 = (item % tiles) << 4, k0 = (item / tiles) * P.kslice;
-    const int ks = min(P.kslice, P.K - k0), pitch = P.kslice * 2 + 64;
-    mbar_expect_tx(bar, 16u * (uint32_t)ks * 2u);
-#pragma unroll 1
-    for (int r = 0; r < 16; ++r) bulk_g2s(buf + r * pitch, P.W + (size_t)(f0 + r) * P.K + k0, (uint32_t)ks * 2u, bar);
-}
-
-template <int NT>
-__device__ __forceinline__ void chain_gemm_item(const ChainPhase& P, int item, const unsigned char* buf, uint64_t* bar,
-                                                uint32_t parity, float* red, int rows, const int* pos) {
-    constexpr int U = NT <= 2 ? 4 : (NT <= 4 ? 2 : 1);
-    constexpr int RP = 8 * NT + 1;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c4 = lane & 3;
-    const int tiles = P.N >> 4, f0 = (item % tiles) << 4, split = item / tiles, k0 = split * P.kslice;
-    const int ks = min(P.kslice, P.K - k0), pitch = P.kslice * 2 + 64;
-    float c[NT][4];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
-    const int nkb = ks >> 5, kbw = (nkb + 3) >> 2;
-    const int kb0 = min(nkb, warp * kbw), kb1 = min(nkb, kb0 + kbw);
-    const __half* xr = P.X16 + (size_t)g * P.K + k0 + 8 * c4;
-    const unsigned char* wr0 = buf + g * pitch + 16 * c4;
-    const unsigned char* wr1 = wr0 + 8 * pitch;
-    bool ready = false;
-    for (int kb = kb0; kb < kb1; kb += U) {
-        uint4 xv[U][NT];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int j = 0; j < NT; ++j)
-                xv[u][j] = (kb + u < kb1) ? __ldcg(reinterpret_cast<const uint4*>(xr + (size_t)(8 * j) * P.K + (size_t)(kb + u) * 32))
-                                          : make_uint4(0, 0, 0, 0);
-        if (!ready) { mbar_wait(bar, parity); ready = true; }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (kb + u < kb1) {
-                const uint4 wa = *reinterpret_cast<const uint4*>(wr0 + (kb + u) * 64);
-                const uint4 wb = *reinterpret_cast<const uint4*>(wr1 + (kb + u) * 64);
-#pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    mma16816(c[j], wa.x, wb.x, wa.y, wb.y, xv[u][j].x, xv[u][j].y);
-                    mma16816(c[j], wa.z, wb.z, wa.w, wb.w, xv[u][j].z, xv[u][j].w);
-                }
-            }
-        }
-    }
-    if (!ready) mbar_wait(bar, parity);
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        red[(warp * 16 + g) * RP + 8 * j + 2 * c4] = c[j][0];
-        red[(warp * 16 + g) * RP + 8 * j + 2 * c4 + 1] = c[j][1];
-        red[(warp * 16 + g + 8) * RP + 8 * j + 2 * c4] = c[j][2];
-        red[(warp * 16 + g + 8) * RP + 8 * j + 2 * c4 + 1] = c[j][3];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 16 * 8 * NT; idx += 128) {
-        const int row = idx >> 4, feat = idx & 15;
-        if (row >= rows) continue;
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) v += red[(w * 16 + feat) * RP + row];
-        const int n = f0 + feat;
-        if (P.epi == EPI_PARTIAL) {
-            P.out_f32[split * P.split_stride + (size_t)row * P.ld_out + n] = v;
-        } else if (P.epi == EPI_F32) {
-            P.out_f32[(size_t)row * P.ld_out + n] = v;
-        } else if (P.epi == EPI_GELU) {
-            P.out_f16[(size_t)row * P.ld_out + n] = __float2half_rn(gelu_erf(half_round(v)));
-        } else {  // EPI_QKV
-            if (n < P.d) {
-                P.q32[(size_t)row * P.d + n] = v;
-            } else {
-                const int which = (n - P.d) / P.d, nn = n % P.d, h = nn >> 6, dd = nn & 63;
-                __half* cache = which ? P.vc : P.kc;
-                cache[(((size_t)row * P.H + h) * P.cache_len + pos[0]) * 64 + dd] = __float2half_rn(v);
-            }
-        }
-    }
-    __syncthreads();   // red and the weight buffer may be reused
-}
-
-// residual + LayerNorm of one row by one 128-thread CTA (same arithmetic and summation order as lm_ln_kernel)
-__device__ __forceinline__ void chain_ln_row(const ChainPhase& P, int r, float* red) {
-    constexpr int V4 = 8;   // d <= 4096
-    const int d = P.d, d4 = d >> 2;
-    float4* xr = reinterpret_cast<float4*>(P.x + (size_t)r * d);
-    float4 v[V4];
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < V4; ++j) {
-        const int i = threadIdx.x + j * 128;
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < d4) {
-            float4 a = __ldcg(xr + i);
-            for (int sp = 0; sp < P.ln_nsplit; ++sp) {
-                const float4 t = __ldcg(reinterpret_cast<const float4*>(P.part + sp * P.ln_split_stride + (size_t)r * d) + i);
-                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-            }
-            if (P.ln_nsplit) xr[i] = a;
-            v[j] = a;
-            s += (a.x + a.y) + (a.z + a.w);
-        }
-    }
-    const float mean = block_sum(s, red) / d;
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < V4; ++j) {
-        const int i = threadIdx.x + j * 128;
-        if (i < d4) {
-            float cx = v[j].x - mean, cy = v[j].y - mean, cz = v[j].z - mean, cw = v[j].w - mean;
-            q = fmaf(cx, cx, q); q = fmaf(cy, cy, q); q = fmaf(cz, cz, q); q = fmaf(cw, cw, q);
-        }
-    }
-    const float rstd = 1.f / sqrtf(block_sum(q, red + 32) / d + 1e-5f);
-#pragma unroll
-    for (int j = 0; j < V4; ++j) {
-        const int i = threadIdx.x + j * 128;
-        if (i < d4) {
-            const float4 gm = reinterpret_cast<const float4*>(P.gamma)[i], bt = reinterpret_cast<const float4*>(P.beta)[i];
-            __half2 lo = __floats2half2_rn((v[j].x - mean) * rstd * gm.x + bt.x, (v[j].y - mean) * rstd * gm.y + bt.y);
-            __half2 hi = __floats2half2_rn((v[j].z - mean) * rstd * gm.z + bt.z, (v[j].w - mean) * rstd * gm.w + bt.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            reinterpret_cast<uint2*>(P.ln_out + (size_t)r * d)[i] = pk;
-        }
-    }
-    __syncthreads();   // red reusable
-}
-
-template <int NT>
-__global__ void __launch_bounds__(128) lm_chain_kernel(ChainParams cp) {
-    constexpr int RP = 8 * NT + 1;
-    extern __shared__ __align__(128) unsigned char csm[];
-    unsigned char* buf[2] = {csm, csm + cp.slab_bytes};
-    uint64_t* bars = reinterpret_cast<uint64_t*>(csm + 2 * (size_t)cp.slab_bytes);
-    float* red = reinterpret_cast<float*>(bars + 2);   // max(4*16*RP, 64) floats
-    const int tid = threadIdx.x, cta = blockIdx.x, G = gridDim.x;
-    uint32_t uses[2] = {0u, 0u};
-
-    if (tid == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
-    __syncthreads();
-    // the GEMM phases this CTA will run, and the two first slabs (weights do not depend on earlier kernels)
-    auto next_gemm = [&](int from) { int q = from; while (q < cp.nph && cp.ph[q].kind != PH_GEMM) ++q; return q; };
-    auto prefetch = [&](int ph, int b) {   // first item of GEMM phase `ph` into buffer b (thread 0)
-        if (ph < cp.nph && tid == 0) {
-            const ChainPhase& Q = cp.ph[ph];
-            if (cta < (Q.N >> 4) * Q.nsplit) chain_issue(Q, cta, buf[b], bars + b);
-        }
-    };
-    int g_next = next_gemm(0);
-    prefetch(g_next, 0);
-    int g_next2 = next_gemm(g_next + 1);
-    prefetch(g_next2, 1);
-    pdl_trigger();
-    pdl_wait();
-
-    int cur = 0;
-    for (int ph = 0; ph < cp.nph; ++ph) {
-        const ChainPhase& P = cp.ph[ph];
-        if (P.kind == PH_GEMM) {
-            const int n_items = (P.N >> 4) * P.nsplit;
-            bool first = true;
-            for (int item = cta; item < n_items; item += G) {
-                if (!first && tid == 0) chain_issue(P, item, buf[cur], bars + cur);
-                chain_gemm_item<NT>(P, item, buf[cur], bars + cur, uses[cur] & 1u, red, cp.rows, cp.pos);
-                ++uses[cur];
-                first = false;
-            }
-            // this buffer is free again: fetch the first slab of the GEMM phase after next
-            const int g3 = next_gemm(g_next2 + 1);
-            prefetch(g3, cur);
-            g_next = g_next2; g_next2 = g3;
-            cur ^= 1;
-        } else {
-            if (cta < cp.rows) chain_ln_row(P, cta, red);
-        }
-        if (ph + 1 < cp.nph) {   // grid barrier
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                atomicAdd(cp.bar, 1u);
-                const unsigned target = (unsigned)(ph + 1) * (unsigned)G;
-                while (ld_acquire_gpu_u32(cp.bar) < target) { }
-            }
-            __syncthreads();
-        }
-    }
-    (void)RP;
-}
-
 __global__ void lm_f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n_valid, size_t n_total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_total) dst[i] = __float2half_rn(i < n_valid ? src[i] : 0.f);
@@ -1329,22 +779,16 @@ struct acb_lm {
     int launches = 0;
     bool has_cross = false;
     bool pdl = true;          // programmatic dependent launch between the kernels of a step
-    bool wide = false;        // ACB_LM_STEP=v6: wide cluster GEMMs with LayerNorm folded in (8 kernels/layer; measured slower)
-    bool chain = false;       // GEMM/LN phases between attention kernels run in persistent chain kernels (opt-in)
-    bool fused = false;       // the whole transformer of a step is ONE persistent kernel (lm_step.cu); default when the packed weights are given
+    bool fused = false;       // ACB_LM_STEP=fused / rotary positions: the whole transformer of a step is ONE persistent kernel (lm_step.cu)
     StepLaunch step{};
     unsigned long long* trace = nullptr;   // ACB_LM_STEP_TRACE=1: per-phase %globaltimer stamps of CTA 0
-    int chain_grid = 0, chain_slab = 0;
-    size_t chain_smem = 0;
-    std::vector<ChainPhase> plan;            // host copy of every chain's phases, in launch order
-    std::vector<int> chain_off, chain_len;   // per chain launch: offset / count into plan
     // ACB_LM_TIMING=1 (debug): in-kernel time stamps of the layer-0 GEMMs of a directly enqueued step
     unsigned long long* timing = nullptr;
     struct TimedGemm { const char* what; int ctas; };
     std::vector<TimedGemm> timed;
 };
 constexpr int ACB_TIMING_MAX_CTAS = 1024, ACB_TIMING_MAX_GEMMS = 16;
-constexpr size_t ACB_PLAN_COUNTER_BYTES = 4096;   // first bytes of buffers.plan: one barrier counter per chain launch
+constexpr size_t ACB_PLAN_COUNTER_BYTES = 4096;   // first bytes of buffers.plan: arrival counters of the split-KV attention
 
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its
 // predecessor in the stream is still running and synchronises itself with griddepcontrol.wait.
@@ -1456,124 +900,6 @@ static int env_int(const char* name, int dflt) {
 
 #define ACB_TRY(expr) do { int rc_ = (expr); if (rc_ != ACB_OK) return rc_; } while (0)
 
-template <int NT>
-static cudaError_t chain_attr(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(lm_chain_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lm_chain_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-}
-template <int NT>
-static cudaError_t chain_occupancy(size_t smem, int* per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, lm_chain_kernel<NT>, 128, smem);
-}
-
-// Build the phase lists of every chain launch of one decode step for the current (rows, cross) configuration and
-// upload them to the caller-owned plan buffer.  Chains are cut at the attention kernels:
-//   chain 0            : LN1(0) QKV(0)
-//   per layer (cross)  : [O LNc CQ]   and   [CO LN2 FFN1 FFN2 LN1(l+1) QKV(l+1)]   (last layer: ... LNout heads)
-//   per layer (no cross): [O LN2 FFN1 FFN2 LN1(l+1) QKV(l+1)]
-static int build_chain_plan(acb_lm* lm, cudaStream_t s) {
-    const acb_lm_config& c = lm->cfg;
-    const acb_lm_buffers& B = lm->buf;
-    const int d = c.dim, ffn = c.ffn_dim, L = c.num_layers, H = c.num_heads, rows = lm->rows, nt = nt_for_rows(rows);
-    const size_t part_stride = (size_t)lm->rows_pad * d;
-    const size_t kv_layer = (size_t)c.max_rows * H * c.max_seq * 64;
-    const int max_kslice = d <= 1536 ? 1536 : 2048;
-    lm->chain_slab = 16 * (max_kslice * 2 + 64);
-    lm->chain_smem = 2 * (size_t)lm->chain_slab + 2 * sizeof(uint64_t) + (size_t)max(4 * 16 * (8 * nt + 1), 64) * sizeof(float);
-    cudaError_t e;
-    int per_sm = 0;
-    switch (nt) {
-        case 1: e = chain_attr<1>(lm->chain_smem); if (e == cudaSuccess) e = chain_occupancy<1>(lm->chain_smem, &per_sm); break;
-        case 2: e = chain_attr<2>(lm->chain_smem); if (e == cudaSuccess) e = chain_occupancy<2>(lm->chain_smem, &per_sm); break;
-        case 4: e = chain_attr<4>(lm->chain_smem); if (e == cudaSuccess) e = chain_occupancy<4>(lm->chain_smem, &per_sm); break;
-        default: e = chain_attr<8>(lm->chain_smem); if (e == cudaSuccess) e = chain_occupancy<8>(lm->chain_smem, &per_sm); break;
-    }
-    ACB_CHECK_CUDA(e);
-    ACB_REQUIRE(per_sm >= 1, "chain kernel does not fit an SM (%zu B smem)", lm->chain_smem);
-    lm->chain_grid = lm->sms * min(per_sm, 2);   // every CTA must be resident: the phases synchronise with a spin barrier
-    const int G = lm->chain_grid;
-
-    lm->plan.clear(); lm->chain_off.clear(); lm->chain_len.clear();
-    int pending = 0;
-    auto begin_chain = [&]() { lm->chain_off.push_back((int)lm->plan.size()); };
-    auto end_chain = [&]() { lm->chain_len.push_back((int)lm->plan.size() - lm->chain_off.back()); };
-    auto ln = [&](const float* gamma, const float* beta) {
-        ChainPhase P{};
-        P.kind = PH_LN; P.d = d; P.x = B.x; P.part = B.part; P.ln_nsplit = pending; P.ln_split_stride = part_stride;
-        P.gamma = gamma; P.beta = beta; P.ln_out = (__half*)B.h16;
-        lm->plan.push_back(P);
-        pending = 0;
-    };
-    auto gemm = [&](const __half* W, const void* X16, int N, int K, int epi, bool split) -> ChainPhase& {
-        ChainPhase P{};
-        P.kind = PH_GEMM; P.W = W; P.X16 = (const __half*)X16; P.N = N; P.K = K; P.epi = epi; P.d = d; P.H = H;
-        const int nkb = K / 32, tiles = N / 16;
-        int ns = acb_ceil_div(K, max_kslice);
-        if (split) ns = max(ns, min(G / tiles, ACB_LM_MAX_SPLIT));
-        ns = max(1, min(ns, nkb));
-        const int kbs = acb_ceil_div(nkb, ns);
-        P.nsplit = acb_ceil_div(nkb, kbs);
-        P.kslice = kbs * 32;
-        if (epi == EPI_PARTIAL) { P.out_f32 = B.part; P.ld_out = N; P.split_stride = part_stride; }
-        lm->plan.push_back(P);
-        return lm->plan.back();
-    };
-    auto qkv_or_heads = [&](int l) {   // LN1(l) + QKV(l), or the output norm + heads after the last layer
-        if (l < L) {
-            const float* lnp = lm->w.ln + (size_t)l * 6 * d;
-            ln(lnp, lnp + d);
-            ChainPhase& P = gemm((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, B.h16, 3 * d, d, EPI_QKV, false);
-            P.q32 = B.q32; P.kc = (__half*)B.k_cache + l * kv_layer; P.vc = (__half*)B.v_cache + l * kv_layer; P.cache_len = c.max_seq;
-        } else {
-            ln(lm->w.out_norm, lm->w.out_norm + d);
-            ChainPhase& P = gemm((const __half*)lm->w.heads, B.h16, c.n_q * c.card, d, EPI_F32, false);
-            P.out_f32 = B.logits; P.ld_out = c.n_q * c.card;
-        }
-    };
-    begin_chain(); qkv_or_heads(0); end_chain();
-    for (int l = 0; l < L; ++l) {
-        const float* lnp = lm->w.ln + (size_t)l * 6 * d;
-        begin_chain();
-        pending = gemm((const __half*)lm->w.w_o + (size_t)l * d * d, B.a16, d, d, EPI_PARTIAL, true).nsplit;
-        if (lm->has_cross) {
-            ln(lnp + 2 * d, lnp + 3 * d);
-            gemm((const __half*)lm->w.w_cq + (size_t)l * d * d, B.h16, d, d, EPI_PARTIAL, true);   // partial queries
-            end_chain();
-            begin_chain();
-            pending = gemm((const __half*)lm->w.w_co + (size_t)l * d * d, B.a16, d, d, EPI_PARTIAL, true).nsplit;
-        }
-        ln(lnp + 4 * d, lnp + 5 * d);
-        {
-            ChainPhase& P = gemm((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, B.h16, ffn, d, EPI_GELU, false);
-            P.out_f16 = (__half*)B.f16; P.ld_out = ffn;
-        }
-        pending = gemm((const __half*)lm->w.w_ff2 + (size_t)l * d * ffn, B.f16, d, ffn, EPI_PARTIAL, true).nsplit;
-        qkv_or_heads(l + 1);
-        end_chain();
-    }
-    const size_t bytes = lm->plan.size() * sizeof(ChainPhase);
-    ACB_REQUIRE(lm->chain_off.size() * sizeof(unsigned) <= ACB_PLAN_COUNTER_BYTES && ACB_PLAN_COUNTER_BYTES + bytes <= ACB_LM_PLAN_BYTES,
-                "chain plan (%zu B) does not fit the plan buffer", bytes);
-    ACB_CHECK_CUDA(cudaMemcpyAsync((unsigned char*)B.plan + ACB_PLAN_COUNTER_BYTES, lm->plan.data(), bytes, cudaMemcpyHostToDevice, s));
-    return ACB_OK;
-}
-
-static int launch_chain(acb_lm* lm, int ci, cudaStream_t s) {
-    ChainParams cp{};
-    cp.ph = reinterpret_cast<const ChainPhase*>((unsigned char*)lm->buf.plan + ACB_PLAN_COUNTER_BYTES) + lm->chain_off[ci];
-    cp.nph = lm->chain_len[ci]; cp.rows = lm->rows; cp.slab_bytes = lm->chain_slab;
-    cp.bar = reinterpret_cast<unsigned*>(lm->buf.plan) + ci; cp.pos = lm->buf.pos;
-    const dim3 grid(lm->chain_grid), block(128);
-    switch (nt_for_rows(lm->rows)) {   // launched WITHOUT the PDL attribute: all CTAs must become resident at once
-        case 1: ACB_LAUNCH(lm_chain_kernel<1>, grid, block, lm->chain_smem, s, false, cp); break;
-        case 2: ACB_LAUNCH(lm_chain_kernel<2>, grid, block, lm->chain_smem, s, false, cp); break;
-        case 4: ACB_LAUNCH(lm_chain_kernel<4>, grid, block, lm->chain_smem, s, false, cp); break;
-        default: ACB_LAUNCH(lm_chain_kernel<8>, grid, block, lm->chain_smem, s, false, cp); break;
-    }
-    return ACB_OK;
-}
-
 // ACB_DEBUG=1: synchronise and report after every launch of a directly-enqueued step (not during graph capture).
 static bool acb_debug_on() {
     static int v = -1;
@@ -1604,8 +930,7 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
 
     if (!gemms_only) {
         ACB_LAUNCH(lm_embed_kernel, dim3(rows), dim3(256), 0, s, pdl, (const __half*)lm->w.emb, lm->w.inv_freq,
-                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale,
-                   (float*)nullptr);
+                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale);
         ++nl;
         DBG("lm_embed_kernel", -1);
     }
@@ -1734,257 +1059,6 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
     return ACB_OK;
 }
 
-// ---- v6 step: wide GEMMs with cluster split-K and LayerNorm folded into producer / consumer (8 kernels per layer)
-struct WTile { int fg, ns, kslice; };
-// Tile plan of one GEMM: 32 features per CTA (16 when N is not a multiple of 32), and K cut into `ns` cluster slices
-// until the slab fits ACB_LM_SLAB_KB (default 56 KB: three CTAs per SM stay co-resident, which is what lets the next
-// kernel's weight prefetch overlap under PDL) and the grid covers ACB_LM_FILL % of the SMs (default 90).
-static WTile pick_wtile(int N, int K, int sms, bool need32) {
-    WTile t;
-    t.fg = (N % 32 == 0 || need32) ? 4 : 2;
-    const int ft = 8 * t.fg, tiles = acb_ceil_div(N, ft), nkb = K / 32;
-    const int slab_cap = env_int("ACB_LM_SLAB_KB", 56) * 1024, fill = env_int("ACB_LM_FILL", 90);
-    int ns = 1;
-    while (ns < 8 && nkb % (2 * ns) == 0 && nkb / (2 * ns) >= 2 &&
-           ((size_t)ft * (K / ns) * 2 > (size_t)slab_cap || tiles * ns * 100 < sms * fill))
-        ns *= 2;
-    t.ns = ns;
-    t.kslice = K / ns;
-    return t;
-}
-
-template <int MT, int FG, bool LNIN, int EPI>
-static cudaError_t wgemm_launch_one(const WGemmParams& p, cudaStream_t s, bool pdl) {
-    const WSmem L = wgemm_smem(MT, FG, LNIN, p.kslice, p.nsplit);
-    static int attr_done = 0;   // per instantiation
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(lm_wgemm_kernel<MT, FG, LNIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(lm_wgemm_kernel<MT, FG, LNIN, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e != cudaSuccess) return e;
-        attr_done = 1;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(acb_ceil_div(p.N, 8 * FG), p.nsplit);
-    cfg.blockDim = dim3(WG_THREADS);
-    cfg.dynamicSmemBytes = (size_t)L.total;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[2];
-    int na = 0;
-    if (p.nsplit > 1) {
-        attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = (unsigned)p.nsplit; attr[na].val.clusterDim.z = 1;
-        ++na;
-    }
-    if (pdl) {
-        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    cfg.attrs = attr; cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, lm_wgemm_kernel<MT, FG, LNIN, EPI>, p);
-}
-template <int FG, bool LNIN, int EPI>
-static cudaError_t wgemm_launch_mt(int mt, const WGemmParams& p, cudaStream_t s, bool pdl) {
-    switch (mt) {
-        case 1: return wgemm_launch_one<1, FG, LNIN, EPI>(p, s, pdl);
-        case 2: return wgemm_launch_one<2, FG, LNIN, EPI>(p, s, pdl);
-        default: return wgemm_launch_one<4, FG, LNIN, EPI>(p, s, pdl);
-    }
-}
-template <bool LNIN, int EPI>
-static int wgemm_launch(int mt, int fg, const WGemmParams& p, cudaStream_t s, bool pdl) {
-    ACB_REQUIRE(wgemm_smem(mt, fg, LNIN, p.kslice, p.nsplit).total <= 200 * 1024,
-                "lm_wgemm: tile needs more than 200 KB of shared memory (N=%d K=%d kslice=%d)", p.N, p.K, p.kslice);
-    if (fg == 4) ACB_CHECK_CUDA((wgemm_launch_mt<4, LNIN, EPI>(mt, p, s, pdl)));
-    else {
-        if constexpr (EPI == WEPI_RESID) { acb_set_error("lm_wgemm: residual tiles must be 32 features wide"); return ACB_ERR_INVALID; }
-        else ACB_CHECK_CUDA((wgemm_launch_mt<2, LNIN, EPI>(mt, p, s, pdl)));
-    }
-    return ACB_OK;
-}
-
-static int mt_for_rows(int rows) { return rows <= 16 ? 1 : (rows <= 32 ? 2 : 4); }
-
-// embed(+stats) | L x [QKV(LN1) | attn | O(+x,stats) | CQ(LNc) | cross-attn | CO(+x,stats) | FFN1(LN2,GELU) | FFN2(+x,stats)]
-// | heads(LNout) | sample.   Statistics live in buffers.part ([d/32 tiles][rows][2] floats); cross queries reuse q32.
-static int enqueue_step_wide(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only, bool capturing) {
-    const acb_lm_config& c = lm->cfg;
-    const acb_lm_buffers& B = lm->buf;
-    const int d = c.dim, ffn = c.ffn_dim, L = c.num_layers, H = c.num_heads, rows = lm->rows, mt = mt_for_rows(rows);
-    const size_t kv_layer = (size_t)c.max_rows * H * c.max_seq * 64;
-    const size_t ckv_layer = (size_t)c.max_rows * H * c.max_text * 64;
-    const float scale = 1.0f / sqrtf(64.f);
-    const bool pdl = lm->pdl;
-    float* stats = B.part;
-    int nl = 0;
-
-    auto base = [&](const void* W, int N, int K, bool need32) {
-        WGemmParams p{};
-        const WTile t = pick_wtile(N, K, lm->sms, need32);
-        p.W = (const __half*)W; p.N = N; p.K = K; p.rows = rows; p.kslice = t.kslice; p.nsplit = t.ns;
-        p.d = d; p.H = H;
-        return std::make_pair(p, t.fg);
-    };
-    if (lm->timing && !capturing) lm->timed.clear();
-    auto tag = [&](WGemmParams& p, int fg, const char* what, int layer) {   // debug time stamps for the layer-0 GEMMs
-        if (!lm->timing || capturing || layer != 0 || (int)lm->timed.size() >= ACB_TIMING_MAX_GEMMS) return;
-        const int ctas = acb_ceil_div(p.N, 8 * fg) * p.nsplit;
-        if (ctas > ACB_TIMING_MAX_CTAS) return;
-        p.timing = lm->timing + (size_t)lm->timed.size() * ACB_TIMING_MAX_CTAS * 8;
-        lm->timed.push_back({what, ctas});
-    };
-    auto with_ln = [&](WGemmParams& p, const float* gamma, const float* beta) {
-        p.X32 = B.x; p.gamma = gamma; p.beta = beta; p.stats_in = stats; p.stat_tiles = d / 32; p.stat_w = 32.f;
-        p.inv_stat_w = 1.f / 32.f; p.inv_k = 1.f / (float)d;
-    };
-    auto resid = [&](const void* W, const void* X16, int K, const char* what, int layer) -> int {
-        auto [p, fg] = base(W, d, K, true);
-        p.X16 = (const __half*)X16; p.x = B.x; p.stats_out = stats;
-        tag(p, fg, what, layer);
-        ACB_TRY((wgemm_launch<false, WEPI_RESID>(mt, fg, p, s, pdl)));
-        ++nl;
-        DBG(what, layer);
-        return ACB_OK;
-    };
-
-    if (!gemms_only) {
-        ACB_LAUNCH(lm_embed_kernel, dim3(rows), dim3(256), 0, s, pdl, (const __half*)lm->w.emb, lm->w.inv_freq,
-                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale, stats);
-        ++nl;
-        DBG("lm_embed_kernel", -1);
-    }
-    for (int l = 0; l < L; ++l) {
-        const float* ln = lm->w.ln + (size_t)l * 6 * d;
-        {   // --- self attention
-            auto [p, fg] = base((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, 3 * d, d, false);
-            with_ln(p, ln, ln + d);
-            p.q32 = B.q32; p.kc = (__half*)B.k_cache + l * kv_layer; p.vc = (__half*)B.v_cache + l * kv_layer;
-            p.cache_len = c.max_seq; p.pos = B.pos;
-            tag(p, fg, "wgemm_QKV", l);
-            ACB_TRY((wgemm_launch<true, WEPI_QKV>(mt, fg, p, s, pdl))); ++nl;
-            DBG("wgemm_QKV", l);
-        }
-        if (!gemms_only) {
-            AttnParams a{B.q32, 1, 0, (__half*)B.k_cache + l * kv_layer, (__half*)B.v_cache + l * kv_layer, (__half*)B.a16,
-                         H, d, c.max_seq, B.pos, 0, scale};
-            ACB_LAUNCH(lm_attn_kernel<false>, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
-            ++nl;
-            DBG("lm_attn_kernel", l);
-        }
-        ACB_TRY(resid((const __half*)lm->w.w_o + (size_t)l * d * d, B.a16, d, "wgemm_O", l));
-        if (lm->has_cross) {   // --- cross attention
-            {
-                auto [p, fg] = base((const __half*)lm->w.w_cq + (size_t)l * d * d, d, d, false);
-                with_ln(p, ln + 2 * d, ln + 3 * d);
-                p.out_f32 = B.q32; p.ld_out = d;
-                tag(p, fg, "wgemm_CQ", l);
-                ACB_TRY((wgemm_launch<true, WEPI_F32>(mt, fg, p, s, pdl))); ++nl;
-                DBG("wgemm_CQ", l);
-            }
-            if (!gemms_only) {
-                AttnParams a{B.q32, 1, 0, (__half*)B.ck_cache + l * ckv_layer, (__half*)B.cv_cache + l * ckv_layer,
-                             (__half*)B.a16, H, d, c.max_text, B.pos, lm->text_len, scale};
-                ACB_LAUNCH(lm_cross_attn_kernel, dim3(acb_ceil_div(rows * H, 8)), dim3(256), 0, s, pdl, a, rows);
-                ++nl;
-                DBG("lm_cross_attn_kernel", l);
-            }
-            ACB_TRY(resid((const __half*)lm->w.w_co + (size_t)l * d * d, B.a16, d, "wgemm_CO", l));
-        }
-        {   // --- feed forward
-            auto [p, fg] = base((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, ffn, d, false);
-            with_ln(p, ln + 4 * d, ln + 5 * d);
-            p.out_f16 = (__half*)B.f16; p.ld_out = ffn;
-            tag(p, fg, "wgemm_FFN1", l);
-            ACB_TRY((wgemm_launch<true, WEPI_GELU>(mt, fg, p, s, pdl))); ++nl;
-            DBG("wgemm_FFN1", l);
-        }
-        ACB_TRY(resid((const __half*)lm->w.w_ff2 + (size_t)l * d * ffn, B.f16, ffn, "wgemm_FFN2", l));
-    }
-    {
-        const int N = c.n_q * c.card;
-        auto [p, fg] = base(lm->w.heads, N, d, false);
-        with_ln(p, lm->w.out_norm, lm->w.out_norm + d);
-        p.out_f32 = B.logits; p.ld_out = N;
-        ACB_TRY((wgemm_launch<true, WEPI_F32>(mt, fg, p, s, pdl))); ++nl;
-        DBG("wgemm_heads", -1);
-    }
-    if (!gemms_only) {
-        int NP = 1;
-        while (NP < c.card) NP <<= 1;
-        SampleParams sp{B.logits, lm->samp.noise_from_buffer ? B.noise : nullptr, logits_out, B.seq, B.seq_mask, B.pos,
-                        c.max_seq, nullptr, lm->batch, rows, c.n_q, c.card, NP, lm->samp.use_sampling, lm->samp.top_k,
-                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0, lm->samp.cfg_coef_beta};
-        size_t smem = ((size_t)c.card + 2 * (size_t)NP) * sizeof(float);
-        ACB_LAUNCH(lm_sample_kernel, dim3(c.n_q, lm->batch), dim3(1024), smem, s, pdl, sp);
-        ++nl;
-        DBG("lm_sample_kernel", -1);
-    }
-    if (n_launch) *n_launch = nl;
-    return ACB_OK;
-}
-
-// Decode step with chain kernels: embed | chain0 | L x [attn | chainX | cross-attn | chainY] | sample.
-static int enqueue_step_chain(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool chains_only, bool capturing) {
-    const acb_lm_config& c = lm->cfg;
-    const acb_lm_buffers& B = lm->buf;
-    const int d = c.dim, L = c.num_layers, H = c.num_heads, rows = lm->rows;
-    const size_t part_stride = (size_t)lm->rows_pad * d;
-    const size_t kv_layer = (size_t)c.max_rows * H * c.max_seq * 64;
-    const size_t ckv_layer = (size_t)c.max_rows * H * c.max_text * 64;
-    const float scale = 1.0f / sqrtf(64.f);
-    const bool pdl = lm->pdl;
-    int nl = 0, ci = 0;
-    // one barrier counter per chain launch, cleared at the start of the step (a memset node in the graph)
-    ACB_CHECK_CUDA(cudaMemsetAsync(B.plan, 0, lm->chain_off.size() * sizeof(unsigned), s));
-    if (!chains_only) {
-        ACB_LAUNCH(lm_embed_kernel, dim3(rows), dim3(256), 0, s, false, (const __half*)lm->w.emb, lm->w.inv_freq,
-                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale,
-                   (float*)nullptr);
-        ++nl;
-        DBG("lm_embed_kernel", -1);
-    }
-    ACB_TRY(launch_chain(lm, ci++, s)); ++nl;
-    DBG("lm_chain_kernel(0)", -1);
-    for (int l = 0; l < L; ++l) {
-        if (!chains_only) {
-            AttnParams a{B.q32, 1, 0, (__half*)B.k_cache + l * kv_layer, (__half*)B.v_cache + l * kv_layer, (__half*)B.a16,
-                         H, d, c.max_seq, B.pos, 0, scale};
-            ACB_LAUNCH(lm_attn_kernel<false>, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
-            ++nl;
-            DBG("lm_attn_kernel", l);
-        }
-        ACB_TRY(launch_chain(lm, ci++, s)); ++nl;
-        DBG("lm_chain_kernel(X)", l);
-        if (lm->has_cross) {
-            if (!chains_only) {
-                const ChainPhase& cq = lm->plan[lm->chain_off[ci - 1] + lm->chain_len[ci - 1] - 1];   // the CQ GEMM
-                AttnParams a{B.part, cq.nsplit, part_stride, (__half*)B.ck_cache + l * ckv_layer,
-                             (__half*)B.cv_cache + l * ckv_layer, (__half*)B.a16, H, d, c.max_text, B.pos, lm->text_len,
-                             scale};
-                ACB_LAUNCH(lm_cross_attn_kernel, dim3(acb_ceil_div(rows * H, 8)), dim3(256), 0, s, pdl, a, rows);
-                ++nl;
-                DBG("lm_cross_attn_kernel", l);
-            }
-            ACB_TRY(launch_chain(lm, ci++, s)); ++nl;
-            DBG("lm_chain_kernel(Y)", l);
-        }
-    }
-    if (!chains_only) {
-        int NP = 1;
-        while (NP < c.card) NP <<= 1;
-        SampleParams sp{B.logits, lm->samp.noise_from_buffer ? B.noise : nullptr, logits_out, B.seq, B.seq_mask, B.pos,
-                        c.max_seq, nullptr, lm->batch, rows, c.n_q, c.card, NP, lm->samp.use_sampling, lm->samp.top_k,
-                        lm->samp.temp, lm->samp.top_p, lm->samp.cfg_coef, lm->samp.seed, 0, lm->samp.cfg_coef_beta};
-        size_t smem = ((size_t)c.card + 2 * (size_t)NP) * sizeof(float);
-        ACB_LAUNCH(lm_sample_kernel, dim3(c.n_q, lm->batch), dim3(1024), smem, s, false, sp);
-        ++nl;
-        DBG("lm_sample_kernel", -1);
-    }
-    if (n_launch) *n_launch = nl;
-    return ACB_OK;
-}
-
 // Fused step: [memset of the barrier counter] -> lm_step_kernel (embed ... logits) -> lm_sample_kernel.
 static int enqueue_step_fused(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool step_only, bool capturing) {
     const acb_lm_config& c = lm->cfg;
@@ -2011,9 +1085,7 @@ static int enqueue_step_fused(acb_lm* lm, cudaStream_t s, float* logits_out, int
 static int enqueue_step(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only = false,
                         bool capturing = false) {
     if (lm->fused) return enqueue_step_fused(lm, s, logits_out, n_launch, gemms_only, capturing);
-    if (lm->chain) return enqueue_step_chain(lm, s, logits_out, n_launch, gemms_only, capturing);
-    return lm->wide ? enqueue_step_wide(lm, s, logits_out, n_launch, gemms_only, capturing)
-                    : enqueue_step_kernels(lm, s, logits_out, n_launch, gemms_only, capturing);
+    return enqueue_step_kernels(lm, s, logits_out, n_launch, gemms_only, capturing);
 }
 
 extern "C" int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, const acb_lm_buffers* buf, acb_lm_t** out) {
@@ -2121,30 +1193,26 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
     {
         const char* e = getenv("ACB_NO_PDL");
         lm->pdl = !(e && e[0] == '1');
-        // persistent chain kernels are an opt-in experiment: measured SLOWER than one kernel per phase on B200
-        // (profiles/r1_perf_step_v5_chain_slower.log, r1_ncu_chain_kernel_raw.csv), see DESIGN.md section 3.1
         if (env_int("ACB_LM_TIMING", 0) && !lm->timing) {
             ACB_CHECK_CUDA(cudaMalloc(&lm->timing, (size_t)ACB_TIMING_MAX_GEMMS * ACB_TIMING_MAX_CTAS * 64));
             ACB_CHECK_CUDA(cudaMemset(lm->timing, 0, (size_t)ACB_TIMING_MAX_GEMMS * ACB_TIMING_MAX_CTAS * 64));
         }
         const char* ev = getenv("ACB_LM_STEP");
-        lm->wide = ev && ev[0] == 'v' && ev[1] == '6';
-        // default: the persistent fused step (needs the packed weights); ACB_LM_STEP=v5 selects one kernel per phase
-        lm->fused = lm->w.wp_qkv != nullptr && !(ev && ev[0] == 'v');
+        // The persistent fused step (lm_step.cu; needs the packed weights) is OPT-IN: ACB_LM_STEP=fused, or a model with rotary
+        // positions (only built there).  Measured 3.1 ms vs 2.03 ms per step at KV length 1 for the per-phase graph below
+        // (~2.3 us of grid barrier + skew per phase against 0.9 us per PDL kernel boundary).
+        lm->fused = lm->w.wp_qkv != nullptr && ((ev && ev[0] == 'f') || c.positional_embedding != 0);
         ACB_REQUIRE(c.positional_embedding == 0 || lm->fused, "acb_lm_begin: rotary positions are built in the fused decode step only");
         if (lm->fused) {
             ACB_TRY(lm_step_prepare(c, lm->w, lm->buf, rows, batch, text_len, lm->has_cross, lm->sms, &lm->step));
             if (env_int("ACB_LM_COOP", 1) == 0) lm->step.cooperative = false;
             if (env_int("ACB_LM_STEP_TRACE", 0)) {
-                if (!lm->trace) ACB_CHECK_CUDA(cudaMalloc(&lm->trace, 4096 * sizeof(unsigned long long)));
-                ACB_CHECK_CUDA(cudaMemset(lm->trace, 0, 4096 * sizeof(unsigned long long)));
-                ACB_REQUIRE(lm->step.n_phases + 2 <= 4096, "trace buffer too small");
+                if (!lm->trace) ACB_CHECK_CUDA(cudaMalloc(&lm->trace, 8192 * sizeof(unsigned long long)));
+                ACB_CHECK_CUDA(cudaMemset(lm->trace, 0, 8192 * sizeof(unsigned long long)));
+                ACB_REQUIRE(lm->step.n_phases + 2 <= 1024, "trace buffer too small");
             }
         }
-        const char* ec = getenv("ACB_LM_CHAIN");
-        lm->chain = (ec && ec[0] == '1') && lm->buf.plan != nullptr;
-        if (lm->chain) ACB_TRY(build_chain_plan(lm, s));
-        else if (lm->buf.plan) ACB_CHECK_CUDA(cudaMemsetAsync(lm->buf.plan, 0, ACB_PLAN_COUNTER_BYTES, s));   // split-KV arrival counters
+        if (lm->buf.plan) ACB_CHECK_CUDA(cudaMemsetAsync(lm->buf.plan, 0, ACB_PLAN_COUNTER_BYTES, s));   // split-KV arrival counters
     }
     for (int attempt = 0; attempt < 2; ++attempt) {
         drop_graph(lm);
@@ -2186,32 +1254,6 @@ extern "C" int acb_lm_steps(acb_lm_t* lm, int n_steps, void* stream) {
     ACB_REQUIRE(lm && lm->exec, "acb_lm_steps: call acb_lm_begin first");
     ACB_REQUIRE(n_steps >= 0, "acb_lm_steps: negative step count");
     for (int i = 0; i < n_steps; ++i) ACB_CHECK_CUDA(cudaGraphLaunch(lm->exec, (cudaStream_t)stream));
-    return ACB_OK;
-}
-
-// Debug report of the in-kernel time stamps (ACB_LM_TIMING=1): per timed GEMM, the spread of CTA start times and the
-// median / max cycles from CTA start to each stamp.
-static int report_timing(acb_lm* lm, cudaStream_t s) {
-    ACB_CHECK_CUDA(cudaStreamSynchronize(s));
-    std::vector<unsigned long long> h((size_t)ACB_TIMING_MAX_CTAS * 8);
-    static const char* names[8] = {"", "start", "pdl_wait", "stats", "slab", "loop", "cluster", "end"};
-    for (size_t gi = 0; gi < lm->timed.size(); ++gi) {
-        const int n = lm->timed[gi].ctas;
-        ACB_CHECK_CUDA(cudaMemcpy(h.data(), lm->timing + gi * ACB_TIMING_MAX_CTAS * 8, (size_t)n * 64, cudaMemcpyDeviceToHost));
-        unsigned long long g0 = ~0ull, g1 = 0;
-        for (int i = 0; i < n; ++i) { g0 = std::min(g0, h[i * 8]); g1 = std::max(g1, h[i * 8]); }
-        fprintf(stderr, "[acb timing] %-11s %4d CTAs, start spread %llu ns;  cycles since CTA start (median/max):", lm->timed[gi].what, n, g1 - g0);
-        for (int sl = 2; sl < 8; ++sl) {
-            std::vector<long long> v;
-            for (int i = 0; i < n; ++i)
-                if (h[i * 8 + sl] > h[i * 8 + 1]) v.push_back((long long)(h[i * 8 + sl] - h[i * 8 + 1]));
-            if (v.empty()) continue;
-            std::sort(v.begin(), v.end());
-            fprintf(stderr, "  %s %lld/%lld", names[sl], v[v.size() / 2], v.back());
-        }
-        fprintf(stderr, "\n");
-    }
-    ACB_CHECK_CUDA(cudaMemset(lm->timing, 0, (size_t)ACB_TIMING_MAX_GEMMS * ACB_TIMING_MAX_CTAS * 64));
     return ACB_OK;
 }
 
@@ -2270,7 +1312,41 @@ static int report_step_trace(acb_lm* lm, cudaStream_t s) {
     for (int k = 0; k < per; ++k)
         fprintf(stderr, "  %s %.2f (%.2f)", cross ? names_c[k] : names_n[k], sum[k] * 1e-3 / lm->cfg.num_layers, mx[k] * 1e-3);
     fprintf(stderr, "\n");
-    ACB_CHECK_CUDA(cudaMemset(lm->trace, 0, 4096 * sizeof(unsigned long long)));
+    {   // sub-steps of the GEMM phases (the CTA running item 0): ns from phase start to stats / A-load done / MMAs issued / accumulator ready / epilogue done
+        std::vector<unsigned long long> f(8192);
+        ACB_CHECK_CUDA(cudaMemcpy(f.data(), lm->trace, 8192 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        static const int gk_c[6] = {0, 2, 4, 6, 8, 10}, gk_n[4] = {0, 2, 4, 6};
+        const int ng = cross ? 6 : 4;
+        fprintf(stderr, "[acb step trace] GEMM sub-steps, mean ns after the phase's first stamp [stats, aload, mma-issued, acc-ready, epilogue]; first stamp - barrier stamp:\n");
+        for (int gi = 0; gi < ng; ++gi) {
+            const int k = cross ? gk_c[gi] : gk_n[gi];
+            double acc[6] = {0}; int cnt = 0; double lag = 0;
+            for (int l = 0; l < lm->cfg.num_layers; ++l) {
+                const int ph = 1 + l * per + k;          // barrier count when the phase starts
+                if (1024 + 8 * ph + 5 >= 8192) break;
+                const unsigned long long* q = f.data() + 1024 + 8 * ph;
+                if (!q[0] || !q[5]) continue;
+                for (int j = 1; j < 6; ++j) acc[j] += q[j] ? (double)(q[j] - q[0]) : 0.0;
+                lag += (double)q[0] - (double)h[ph];
+                ++cnt;
+            }
+            if (cnt) fprintf(stderr, "    %-4s  %.0f %.0f %.0f %.0f %.0f   (start lag %.0f ns, %d layers)\n", cross ? names_c[k] : names_n[k],
+                             acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt, acc[5] / cnt, lag / cnt, cnt);
+        }
+    }
+    {   // per-K-block stamps of the layer-1 QKV and FF2 GEMMs: [loop top -> full barrier passed -> MMAs + commit issued]
+        std::vector<unsigned long long> f(8192);
+        ACB_CHECK_CUDA(cudaMemcpy(f.data(), lm->trace, 8192 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int which = 0; which < 2; ++which) {
+            const unsigned long long* q = f.data() + 6000 + which * 64;
+            if (!q[0]) continue;
+            fprintf(stderr, "[acb step trace] %s layer 1, per K block ns since loop start (top, data ready, issued):", which ? "ff2" : "qkv");
+            for (int kb = 0; kb < 12 && q[3 * kb]; ++kb)
+                fprintf(stderr, "  [%lld %lld %lld]", (long long)(q[3 * kb] - q[0]), (long long)(q[3 * kb + 1] - q[0]), (long long)(q[3 * kb + 2] - q[0]));
+            fprintf(stderr, "\n");
+        }
+    }
+    ACB_CHECK_CUDA(cudaMemset(lm->trace, 0, 8192 * sizeof(unsigned long long)));
     return ACB_OK;
 }
 
@@ -2280,8 +1356,7 @@ extern "C" int acb_lm_step_logits(acb_lm_t* lm, float* logits_out, void* stream)
     ACB_TRY(enqueue_step(lm, (cudaStream_t)stream, logits_out, nullptr));
     if (lm->fused && lm->trace) { lm->step.p.trace = nullptr; ACB_TRY(report_step_trace(lm, (cudaStream_t)stream)); }
     if (lm->fused) return ACB_OK;
-    if (lm->timing && !lm->wide && !lm->chain) ACB_TRY(report_timeline(lm, (cudaStream_t)stream));
-    if (lm->timing && lm->wide && !lm->chain) ACB_TRY(report_timing(lm, (cudaStream_t)stream));
+    if (lm->timing) ACB_TRY(report_timeline(lm, (cudaStream_t)stream));
     return ACB_OK;
 }
 

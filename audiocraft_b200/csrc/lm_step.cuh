@@ -24,6 +24,7 @@ struct StepParams {
     __half* kc; __half* vc; const __half* ckc; const __half* cvc;
     const int64_t* seq; const int* pos; unsigned* bar;
     unsigned long long* trace;   // debug: CTA 0 stamps %globaltimer after every grid barrier (NULL: off)
+    int l2_ahead;                // tiles the producer's L2-prefetch cursor runs ahead of its ring cursor
     int stop_after, max_gemms;   // debug (ACB_LM_STEP_STOP): leave the kernel after this many grid barriers
     int sin_pos, rope;           // positional_embedding: 'sin' (1,0), 'rope' (0,1), 'sin_rope' (1,1)  (transformer.py:632-637, 701-705)
     const float* rope_freq;      // [32] 1 / max_period^(2i/64), RotaryEmbedding.frequencies (rope.py:68-69)

@@ -383,6 +383,12 @@ class EncodecModel(CompressionModel):
             codes = codes.to(self.device, torch.int64).contiguous()
             B, K, T = codes.shape
             assert K <= self.max_n_q
+            # F.embedding in the reference (core_vq.py:177-179) raises on an out-of-range index; the gather kernel would
+            # clamp, so refuse here (one host sync per decode)
+            if codes.numel():
+                lo, hi = int(codes.min()), int(codes.max())
+                if lo < 0 or hi >= self.bins:
+                    raise IndexError(f"codes out of range [0, {self.bins}): min {lo}, max {hi}")
             out = torch.empty((B, self.dimension, T), device=self.device, dtype=torch.float32)
             _lib.check(self._lib.acb_rvq_decode(_lib.ptr(codes), _lib.ptr(self.codebooks), _lib.ptr(out), B,
                                                 self.dimension, T, K, self.bins, _lib.stream()), 'rvq_decode')

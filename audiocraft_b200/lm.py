@@ -94,11 +94,14 @@ class LMModel:
         w['ln'] = ln
         w['out_norm'] = torch.stack([sd['out_norm.weight'].float(), sd['out_norm.bias'].float()]).to(dev).contiguous()
         w['heads'] = torch.cat([h(sd[f'linears.{k}.weight']) for k in range(self.n_q)], dim=0).contiguous()
-        # the persistent fused step streams 128 x 64 tiles in the tensor-core operand layout: re-pack once at load time
-        # (acb_lm_pack_weight); shapes that do not tile (N % 128, K % 64) keep the per-phase kernels
+        # the persistent fused step (opt-in: ACB_LM_STEP=fused, or rotary positions) streams 128 x 64 tiles in the tensor-core
+        # operand layout: re-packed once at load time (acb_lm_pack_weight) when it will be used; shapes that do not tile
+        # (N % 128, K % 64) only have the per-phase kernels
+        import os as _os
         ffn, NH = self.ffn_dim, self.n_q * self.card
         self.fused_ok = d % 128 == 0 and ffn % 128 == 0 and NH % 128 == 0
-        if self.fused_ok:
+        want_fused = _os.environ.get('ACB_LM_STEP', '').startswith('f') or cfg.get('positional_embedding', 'sin') != 'sin'
+        if self.fused_ok and want_fused:
             def pack(name, n, k):
                 src = w[name]
                 if src is None:

@@ -33,6 +33,11 @@ class BaseGenModel:
         if max_duration is None:
             raise ValueError("You must provide max_duration when building directly your GenModel")
         self.name, self.compression_model, self.lm = name, compression_model.eval(), lm.eval()
+        # a code >= bins (or the LM's special token) must never reach the codec: the reference would raise an index error
+        assert lm.card == compression_model.cardinality, \
+            f"LM cardinality {lm.card} != codec cardinality {compression_model.cardinality}"
+        assert lm.n_q == compression_model.num_codebooks, \
+            f"LM codebooks {lm.n_q} != codec codebooks {compression_model.num_codebooks}"
         self.cfg = None
         self.device = lm.device
         self.max_duration = float(max_duration)
@@ -144,12 +149,13 @@ class MusicGen(BaseGenModel):
         self.set_generation_params(duration=15)  # the reference's default duration
 
     @staticmethod
-    def get_pretrained(name: str = 'facebook/musicgen-medium', device=None):
+    def get_pretrained(name: str = 'facebook/musicgen-medium', device=None, text_encoder=None):
         """The reference pulls checkpoints from the HF hub (musicgen.py:56-94); offline this accepts a directory holding
-        the reference's exported `state_dict.bin` + `compression_state_dict.bin`, or `synthetic/<small|medium|large>` for
-        seeded random weights of the released architectures."""
+        the reference's exported `state_dict.bin` + `compression_state_dict.bin` (then `text_encoder`, a callable returning
+        the frozen T5's hidden states and mask, is required: T5 is outside the hot path and not available offline), or
+        `synthetic/<small|medium|large>` for seeded random weights of the released architectures."""
         from .loaders import load_musicgen
-        return load_musicgen(name, device=device)
+        return load_musicgen(name, device=device, text_encoder=text_encoder)
 
     def set_generation_params(self, use_sampling: bool = True, top_k: int = 250, top_p: float = 0.0,
                               temperature: float = 1.0, duration: float = 30.0, cfg_coef: float = 3.0,
@@ -177,9 +183,9 @@ class AudioGen(BaseGenModel):
         self.set_generation_params(duration=5)
 
     @staticmethod
-    def get_pretrained(name: str = 'facebook/audiogen-medium', device=None):
+    def get_pretrained(name: str = 'facebook/audiogen-medium', device=None, text_encoder=None):
         from .loaders import load_audiogen
-        return load_audiogen(name, device=device)
+        return load_audiogen(name, device=device, text_encoder=text_encoder)
 
     def set_generation_params(self, use_sampling: bool = True, top_k: int = 250, top_p: float = 0.0,
                               temperature: float = 1.0, duration: float = 10.0, cfg_coef: float = 3.0,

@@ -193,37 +193,64 @@ def run_b200(args):
     e2e_value = B * dur * world * max(1, min(args.steps, 2)) / (ms_e2e / 1e3)
     d2h_bytes = wav_host.numel() * 4
 
-    # ---- dominant kernel (lm_gemm_kernel) timed in isolation with CUDA events on the launching stream.
-    # One pass = every weight matrix of one decode step (W_step bytes >> 126 MB L2, so passes do not hit in L2).
+    # ---- dominant kernel, timed in isolation with CUDA events on the launching stream (acb_lm_debug_gemms enqueues only it).
+    # Fused step: the dominant kernel IS the step (lm_step_kernel, one launch per decode step); its algorithmic bytes depend
+    # on the KV length, so it is timed at 5 pinned lengths and the generation is integrated over them (trapezoid).
+    # Per-phase path (ACB_LM_STEP=v5): lm_gemm_kernel, one pass = every weight matrix of a step.
+    # Either way one launch / pass streams W_step = 3.2 GB >> 126 MB L2: no L2 reuse between timed launches.
     rows = 2 * B
     w_step, kv_tok, total_bytes = algorithmic_bytes(lm, rows, S)
-    nl = C.c_int(0)
-    reps = 20
-    for _ in range(3):
-        _lib.check(lm._lib.acb_lm_debug_gemms(lm._handle, _lib.stream(), C.byref(nl)))
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        _lib.check(lm._lib.acb_lm_debug_gemms(lm._handle, _lib.stream(), C.byref(nl)))
-    e1.record()
-    torch.cuda.synchronize()
-    gemm_ms = e0.elapsed_time(e1) / reps
     pk = peaks()
-    traffic = None   # dram__bytes_read+write of lm_gemm_kernel over one step, from the committed ncu capture
-    tp = os.path.join(ROOT, 'profiles', 'r1_step_kv750_v9_dram_summary.json')   # ncu capture of the current kernels
-    if os.path.exists(tp) and args.scale == 'medium' and B == 8:
-        tj = json.load(open(tp)).get('lm_gemm_kernel')
-        if tj:
-            traffic = int((tj['dram_read_MB'] + tj['dram_write_MB']) * 1e6)
-    achieved = w_step / (gemm_ms / 1e3) / 1e9
-    step_ms = ms / args.steps / (S - 1)  # includes the EnCodec decode, amortised
-    roofline = dict(bound='hbm', kernel='lm_gemm_kernel', achieved=round(achieved, 1), peak=pk['hbm_gbs'], unit='GB/s',
-                    frac=round(achieved / pk['hbm_gbs'], 4), traffic=traffic, peak_source=pk['source'],
-                    launches_per_pass=nl.value, bytes_per_pass=w_step, ms_per_pass=round(gemm_ms, 4),
-                    whole_generate=dict(algorithmic_bytes=total_bytes, achieved=round(total_bytes / (ms / args.steps / 1e3) / 1e9, 1),
-                                        frac=round(total_bytes / (ms / args.steps / 1e3) / 1e9 / pk['hbm_gbs'], 4),
-                                        ms_per_decode_step=round(step_ms, 4)))
+    nl = C.c_int(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fused = lm.launches_per_step <= 4
+
+    def time_dominant(reps):
+        for _ in range(3):
+            _lib.check(lm._lib.acb_lm_debug_gemms(lm._handle, _lib.stream(), C.byref(nl)))
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            _lib.check(lm._lib.acb_lm_debug_gemms(lm._handle, _lib.stream(), C.byref(nl)))
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    traffic = None
+    step_ms = ms / args.steps / (S - 1)  # whole generate incl. sampler and EnCodec decode, amortised per decode step
+    whole = dict(algorithmic_bytes=total_bytes, achieved=round(total_bytes / (ms / args.steps / 1e3) / 1e9, 1),
+                 frac=round(total_bytes / (ms / args.steps / 1e3) / 1e9 / pk['hbm_gbs'], 4), ms_per_decode_step=round(step_ms, 4))
+    if fused:
+        pts = []
+        for t in (0, (S - 2) // 4, (S - 2) // 2, 3 * (S - 2) // 4, S - 2):
+            lm._bufs['pos'][0] = t
+            k_ms = time_dominant(10)
+            byt = w_step + rows * (t + 1) * kv_tok + rows * kv_tok
+            pts.append(dict(kv_len=t + 1, ms=round(k_ms, 4), algorithmic_bytes=byt, gbs=round(byt / k_ms / 1e6, 1)))
+        tot_ms = sum((pts[i]['ms'] + pts[i + 1]['ms']) / 2 * (pts[i + 1]['kv_len'] - pts[i]['kv_len']) for i in range(len(pts) - 1))
+        mid = pts[len(pts) // 2]
+        achieved = total_bytes / (tot_ms / 1e3) / 1e9
+        tp = os.path.join(ROOT, 'profiles', 'r2_step_kernel_dram.json')   # ncu --set full capture of lm_step_kernel at KV 752
+        if os.path.exists(tp) and args.scale == 'medium' and B == 8:
+            tj = json.load(open(tp))
+            traffic = int(tj['dram_bytes_read'] + tj['dram_bytes_write'])
+        roofline = dict(bound='hbm', kernel='lm_step_kernel', achieved=round(achieved, 1), peak=pk['hbm_gbs'], unit='GB/s',
+                        frac=round(achieved / pk['hbm_gbs'], 4), traffic=traffic, peak_source=pk['source'],
+                        how='algorithmic bytes of the S-1 step launches of one generate / their kernel time, the latter integrated '
+                            'from CUDA-event timings of the isolated kernel at the listed KV lengths; traffic = ncu dram bytes of the '
+                            'launch at kv_len ' + str(mid['kv_len']) + ' (algorithmic ' + str(mid['algorithmic_bytes']) + ' B)',
+                        launches_per_generate=S - 1, kernel_ms_per_generate=round(tot_ms, 2), per_kv=pts, whole_generate=whole)
+    else:
+        gemm_ms = time_dominant(20)
+        tp = os.path.join(ROOT, 'profiles', 'r1_step_kv750_v9_dram_summary.json')   # ncu capture of the per-phase kernels
+        if os.path.exists(tp) and args.scale == 'medium' and B == 8:
+            tj = json.load(open(tp)).get('lm_gemm_kernel')
+            if tj:
+                traffic = int((tj['dram_read_MB'] + tj['dram_write_MB']) * 1e6)
+        achieved = w_step / (gemm_ms / 1e3) / 1e9
+        roofline = dict(bound='hbm', kernel='lm_gemm_kernel', achieved=round(achieved, 1), peak=pk['hbm_gbs'], unit='GB/s',
+                        frac=round(achieved / pk['hbm_gbs'], 4), traffic=traffic, peak_source=pk['source'],
+                        launches_per_pass=nl.value, bytes_per_pass=w_step, ms_per_pass=round(gemm_ms, 4), whole_generate=whole)
 
     # ---- secondary metric: EnCodec 32 kHz encode+decode MSamples/s (BASELINE configs[3] per-GPU slice, 32 x 10 s)
     secondary = None

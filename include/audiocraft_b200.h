@@ -232,8 +232,8 @@ int acb_lm_debug_gemms(acb_lm_t* lm, void* stream, int* n_launches);
 int acb_lm_uses_pdl(const acb_lm_t* lm);
 
 /* [N][K] row-major fp16 (N % 128 == 0, K % 64 == 0) -> the packed tile layout of acb_lm_weights.wp_*: tile (nt, kb) =
- * features [128 nt, +128) x K [64 kb, +64) at ((nt * K/64 + kb) * 8192) halves, inside a tile
- * [16-byte k-chunk (8)][feature (128)][8 halves] (the canonical K-major UMMA layout without swizzle). */
+ * features [128 nt, +128) x K [64 kb, +64) at ((nt * K/64 + kb) * 8192) halves; inside a tile feature f is the 128-byte row
+ * at f * 128 and its 16-byte chunk c sits at position c ^ (f & 7) (the canonical 128-byte-swizzled K-major UMMA layout). */
 int acb_lm_pack_weight(const void* w, void* wp, int n, int k, void* stream);
 
 /* Inspection of the fused step's work decomposition: out[4 g + {0,1,2,3}] = N, K, K-splits, 64-element K blocks per item

@@ -52,7 +52,6 @@ def build_ref_lm(cfg: dict, sd: tp.Dict[str, torch.Tensor], table: tp.Dict[str, 
             mask = inputs['mask']
             return self.output_proj(inputs['hid']) * mask.unsqueeze(-1), mask
 
-    prov = cond.ConditioningProvider({'description': StubText(cfg['cond_dim'], cfg['dim'])}, device=device)
     fuser = cond.ConditionFuser({'cross': ['description'], 'sum': [], 'prepend': [], 'input_interpolate': []})
     kw = dict(n_q=cfg['n_q'], card=cfg['card'], dim=cfg['dim'], num_heads=cfg['num_heads'],
               hidden_scale=cfg['hidden_scale'], norm='layer_norm', norm_first=True, bias_proj=False,
@@ -60,14 +59,29 @@ def build_ref_lm(cfg: dict, sd: tp.Dict[str, torch.Tensor], table: tp.Dict[str, 
               memory_efficient=True, cross_attention=True, activation='gelu', positional_embedding='sin', dropout=0.0)
     kw.update(lm_kwargs)
     # builders.py:136-175: device / dtype reach the transformer only; embeddings, heads and the condition provider stay
-    # fp32 and the whole model is moved with .to(device)
-    m = lmm.LMModel(pat.DelayedPatternProvider(cfg['n_q'], delays=cfg['delays']), prov.to(device), fuser,
-                    device=device, dtype=dtype, **kw).to(device)
-    cp_prefix = 'condition_provider.'
-    body = {k: v for k, v in sd.items() if not k.startswith(cp_prefix)}
-    missing, unexpected = m.load_state_dict(body, strict=False)
-    assert not unexpected and all(k.startswith(cp_prefix) or k.endswith('rope.frequencies') for k in missing), (missing, unexpected)
-    m.condition_provider.load_state_dict({k[len(cp_prefix):]: v.float() for k, v in sd.items() if k.startswith(cp_prefix)})
+    # fp32 and the whole model is moved with .to(device).  The modules are CONSTRUCTED on the meta device (no random init
+    # of 1.8-3.3 B parameters just to overwrite them) and the seeded state dict is assigned in with the dtypes the
+    # reference would hold: `dtype` for transformer.* matrices and norms, fp32 for everything else.
+    with torch.device('meta'):
+        prov = cond.ConditioningProvider({'description': StubText(cfg['cond_dim'], cfg['dim'])}, device=device)
+        m = lmm.LMModel(pat.DelayedPatternProvider(cfg['n_q'], delays=cfg['delays']), prov, fuser, dtype=dtype, **kw)
+    want = {k: v.dtype for k, v in m.state_dict().items()}
+    cast = {}
+    for k, v in sd.items():
+        assert k in want, k
+        cast[k] = v.detach().to(device=device, dtype=want[k])
+    missing, unexpected = m.load_state_dict(cast, strict=False, assign=True)
+    assert not unexpected and all(k.endswith('rope.frequencies') for k in missing), (missing, unexpected)
+    for mod in m.modules():                      # buffers created on meta (rope frequencies): recompute like rope.py:68-69
+        for name, buf in list(mod.named_buffers(recurse=False)):
+            if buf.is_meta:
+                if name == 'frequencies':
+                    hd = cfg['dim'] // cfg['num_heads']
+                    adim = torch.arange(0, hd, 2, device=device, dtype=torch.float32)[: hd // 2]
+                    mod.register_buffer(name, 1.0 / (float(kw.get('max_period', 10000.0)) ** (adim / hd)))
+                else:
+                    raise RuntimeError(f'unmaterialised buffer {name}')
+    m.condition_provider.device = device
     return m.eval(), cond.ConditioningAttributes
 
 
