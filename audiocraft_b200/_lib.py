@@ -11,9 +11,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libaudiocraft_b200.so')
 
 CONV_FP32, CONV_TF32X3, CONV_TF32X3_MMASYNC = 0, 1, 2
-CONV_T6_FLUSH = 3   # host-side selector only: layers that qualify go through the EXPERIMENTAL acb_conv1d_t6, the rest fp32
+CONV_T6_FLUSH = 3   # host-side selector only: every layer acb_conv1d_t6 supports goes through it, the rest fp32 FMA
+CONV_T6_AUTO = 4    # host-side selector only: acb_conv1d_t6 where it is faster (k > 1, >= 128 output channels), else fp32 FMA
 ACB_LM_MAX_SPLIT = 8
 ACB_LM_PART_SLOTS = 16
+ACB_LM_PREFILL_ROWS = 64
 ACB_LM_PLAN_BYTES = 2 << 20
 
 
@@ -71,6 +73,7 @@ def lib():
     L.acb_lm_destroy.argtypes = [vp]
     L.acb_lm_begin.argtypes = [vp, vp, ci, ci, ci, ci, C.POINTER(LMSampling), vp]
     L.acb_lm_steps.argtypes = [vp, ci, vp]
+    L.acb_lm_prefill.argtypes = [vp, ci, ci, vp]
     L.acb_lm_step_logits.argtypes = [vp, vp, vp]
     L.acb_lm_launches_per_step.argtypes = [vp]
     L.acb_lm_rows_pad.argtypes = [ci]
@@ -85,7 +88,7 @@ def lib():
                  'acb_rvq_decode', 'acb_lm_create', 'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps',
                  'acb_lm_step_logits', 'acb_lm_launches_per_step', 'acb_lm_rows_pad', 'acb_sample',
                  'acb_device_sm_count', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_debug_chain_latency',
-                 'acb_conv1d_t6', 'acb_conv1d_t6_tile', 'acb_debug_grid_barrier', 'acb_lm_pack_weight', 'acb_lm_debug_step_plan'):
+                 'acb_conv1d_t6', 'acb_conv1d_t6_tile', 'acb_debug_grid_barrier', 'acb_lm_pack_weight', 'acb_lm_debug_step_plan', 'acb_lm_prefill'):
         getattr(L, name).restype = ci
     _lib = L
     return L
@@ -96,7 +99,7 @@ EXPORTS = ['acb_version', 'acb_last_error', 'acb_device_sm_count', 'acb_weight_n
            'acb_lstm_recurrent', 'acb_lstm_state_bytes', 'acb_rvq_encode', 'acb_rvq_decode', 'acb_lm_create',
            'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps', 'acb_lm_step_logits', 'acb_lm_rows_pad',
            'acb_lm_launches_per_step', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_sample', 'acb_debug_chain_latency', 'acb_conv1d_t6', 'acb_conv1d_t6_tile',
-           'acb_debug_grid_barrier', 'acb_lm_pack_weight', 'acb_lm_debug_step_plan']
+           'acb_debug_grid_barrier', 'acb_lm_pack_weight', 'acb_lm_debug_step_plan', 'acb_lm_prefill']
 
 
 def check(rc: int, what: str = ''):

@@ -304,8 +304,8 @@ static int launch_conv1d_tc(const ConvParams& p, int batch, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // conv1d on the 5th-generation tensor cores: tcgen05.mma.kind::tf32 with the accumulator in TMEM, 3xTF32 split.
 //   D[128 time steps (TMEM lanes)][N output channels (TMEM columns)] += A[128][8] . B[N][8]^T   per instruction
-//   A = im2col rows of the staged input slab, B = weight rows, both K-major in the canonical no-swizzle layout
-//       offset(row, k16B) = k16B * LBO + (row / 8) * 128 B + (row % 8) * 16 B      (8x16B core matrices, SBO = 128 B)
+//   A = im2col rows of the staged input slab, B = weight rows, both K-major in the canonical 128-byte-swizzled layout
+//       offset(row, k16B) = row * 128 B + ((k16B ^ (row % 8)) * 16 B)              (one 32-row reduction chunk = one 128-byte row)
 // Per reduction chunk of 32 rows (r = channel x tap) every thread builds its im2col row (hi and lo tf32 parts) and a
 // share of the weight tile, a proxy fence publishes them to the async proxy, ONE thread issues 4 k-steps x 3 MMAs
 // (lo*hi, hi*lo, hi*hi) and commits to an mbarrier; the epilogue reads the accumulator with tcgen05.ld (lane = time
@@ -318,6 +318,16 @@ __device__ __forceinline__ uint64_t t5_desc(uint32_t smem_addr, uint32_t lbo_byt
     // version [46,48) = 1, layout_type [61,64) = 0 (SWIZZLE_NONE)
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
            ((uint64_t)1 << 46);
+}
+// The same descriptor for the 128-byte-swizzled K-major layout (layout_type 2, SBO = 1024 B between 8-row groups, LBO unused):
+// a tile row is 32 fp32 = 128 contiguous bytes and its 16-byte chunk c sits at position c ^ (row & 7); tiles are 1024-byte
+// aligned and a K step of 8 tf32 advances the start address by 32 bytes.  The tensor core fetches un-swizzled (INTERLEAVE)
+// operands 16 bytes per cycle -- measured on the LM step kernel, ~300 cycles per 128x16x16 MMA -- so conv1d_t5 stages its
+// im2col and weight tiles in this layout (conv1d_t6 keeps INTERLEAVE: its taps are descriptor start-address shifts by whole
+// rows, which a swizzled layout would need base-offset arithmetic for).
+__device__ __forceinline__ uint64_t t5_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
 }
 __device__ __forceinline__ void t5_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
@@ -342,7 +352,7 @@ __device__ __forceinline__ void t5_split(float x, float (&out)[TERMS]) {
 template <int TERMS, int NW>   // NW = weight elements per thread and chunk = N * 32 / 256
 __global__ void __launch_bounds__(256, 2) conv1d_t5_kernel(ConvParams p, int xsp) {
     constexpr int N = NW * 8;
-    extern __shared__ __align__(128) unsigned char t5sm[];
+    extern __shared__ __align__(1024) unsigned char t5sm[];   // swizzled operand tiles are 1024-byte aligned
     // [A terms: TERMS x 16 KB][B terms: TERMS x N*128 B][slab][roff][mbar][tmem slot]
     float* a_t = reinterpret_cast<float*>(t5sm);
     float* b_t = a_t + TERMS * T5_M * T5_RC;
@@ -394,7 +404,6 @@ __global__ void __launch_bounds__(256, 2) conv1d_t5_kernel(ConvParams p, int xsp
     const uint32_t tmem = *tslot;
 
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T5_M >> 4) << 24);
-    constexpr uint32_t lbo_a = (T5_M / 8) * 128, lbo_b = (uint32_t)(N / 8) * 128;
     const uint32_t a_s = smem_u32_(a_t), b_s = smem_u32_(b_t);
 
     float xr[T5_SLAB_PT], wr[NW];
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(256, 2) conv1d_t5_kernel(ConvParams p, int xsp
             const int idx = tid + 256 * i, r = idx / N, cc = idx % N;
             float parts[TERMS];
             t5_split<TERMS>(wr[i], parts);
-            const int o = (r >> 2) * (N / 8) * 32 + (cc >> 3) * 32 + (cc & 7) * 4 + (r & 3);   // canonical K-major, in floats
+            const int o = cc * 32 + (((r >> 2) ^ (cc & 7)) << 2) + (r & 3);   // row cc (128 B), chunk r/4 at position (r/4) ^ (cc & 7), in floats
 #pragma unroll
             for (int q = 0; q < TERMS; ++q) b_t[q * N * T5_RC + o] = parts[q];
         }
@@ -436,7 +445,7 @@ __global__ void __launch_bounds__(256, 2) conv1d_t5_kernel(ConvParams p, int xsp
                 float parts[4][TERMS];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) t5_split<TERMS>(xs[roff[rbase + kc * 4 + e] + t], parts[e]);
-                const int o = ((rbase >> 2) + kc) * (T5_M / 8) * 32 + (t >> 3) * 32 + (t & 7) * 4;   // in floats
+                const int o = t * 32 + ((((rbase >> 2) + kc) ^ (t & 7)) << 2);   // row t (128 B), chunk at position chunk ^ (t & 7), in floats
 #pragma unroll
                 for (int q = 0; q < TERMS; ++q)
                     *reinterpret_cast<float4*>(a_t + q * T5_M * T5_RC + o) =
@@ -452,8 +461,8 @@ __global__ void __launch_bounds__(256, 2) conv1d_t5_kernel(ConvParams p, int xsp
                 uint64_t ad[TERMS], bd[TERMS];
 #pragma unroll
                 for (int q = 0; q < TERMS; ++q) {
-                    ad[q] = t5_desc(a_s + q * (T5_M * T5_RC * 4) + ks * 2 * lbo_a, lbo_a);
-                    bd[q] = t5_desc(b_s + q * (N * T5_RC * 4) + ks * 2 * lbo_b, lbo_b);
+                    ad[q] = t5_desc_sw128(a_s + q * (T5_M * T5_RC * 4) + ks * 32);
+                    bd[q] = t5_desc_sw128(b_s + q * (N * T5_RC * 4) + ks * 32);
                 }
                 // smallest cross terms first; term index 0 = hi.  Keep products a_i * b_j with i + j < TERMS.
 #pragma unroll

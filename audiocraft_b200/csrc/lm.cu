@@ -102,13 +102,15 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 
 // ------------------------------------------------------------------------------------------------ embed + sin pos
 // x[r] = sum_k emb_k[seq[b,k,pos]] + pos_scale * [cos(pos/f_i), sin(pos/f_i)]   (lm.py:244, transformer.py:70-89,701-705)
+// PF (prompt prefill): the grid's rows are (token, row) pairs r = tok * rows_real + row at positions P[0] + tok.
+template <bool PF>
 __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict__ emb, const float* __restrict__ inv_freq,
                                                        const int64_t* __restrict__ seq, const int* __restrict__ P,
                                                        float* __restrict__ x, int d, int n_q, int card, int max_seq,
-                                                       int batch, float pos_scale) {
+                                                       int batch, float pos_scale, int rows_real) {
     pdl_trigger();
     pdl_wait();
-    const int r = blockIdx.x, b = r % batch, pos = P[0];
+    const int r = blockIdx.x, b = (PF ? r % rows_real : r) % batch, pos = P[0] + (PF ? r / rows_real : 0);
     __shared__ int tok[16];
     if (threadIdx.x < n_q) {
         long long t = seq[((size_t)b * n_q + threadIdx.x) * max_seq + pos];
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(LN_THREADS) lm_ln_kernel(float* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------ skinny GEMM
-enum { EPI_PARTIAL = 0, EPI_QKV = 1, EPI_GELU = 2, EPI_F32 = 3, EPI_CROSSKV = 4 };
+enum { EPI_PARTIAL = 0, EPI_QKV = 1, EPI_GELU = 2, EPI_F32 = 3, EPI_CROSSKV = 4, EPI_QKV_PF = 5 };   // _PF: prompt prefill, rows are (token, row) pairs
 
 struct GemmParams {
     const __half* W;  // [N][K] fp16, reference layout
@@ -193,6 +195,7 @@ struct GemmParams {
     __half* out_f16;                                   // GELU
     float* q32; __half* kc; __half* vc; int d, H, cache_len; const int* pos;  // QKV / CROSSKV
     int text_len, row0;                                                      // CROSSKV
+    int rows_real;                                                           // QKV_PF: rows of the generation (GEMM row = tok * rows_real + row)
     unsigned long long* timing;                 // debug timeline
 };
 
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
     pdl_wait();   // activations written by the previous kernel are visible from here on
     tl_stamp(p.timing, 1);
     int cache_pos = 0;
-    if (EPI == EPI_QKV) cache_pos = p.pos[0];   // requested now, consumed in the epilogue: off the critical path
+    if (EPI == EPI_QKV || EPI == EPI_QKV_PF) cache_pos = p.pos[0];   // requested now, consumed in the epilogue: off the critical path
 
     float c[FT2][NT][4];
 #pragma unroll
@@ -307,6 +310,15 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
                 __half* cache = which == 2 ? p.vc : p.kc;
                 cache[(((size_t)row * p.H + (nn >> 6)) * p.cache_len + cache_pos) * 64 + (nn & 63)] = __float2half_rn(v);
             }
+        } else if (EPI == EPI_QKV_PF) {   // prefill: row = tok * rows_real + r -> cache row r, position pos + tok
+            const int which = n >= 2 * p.d ? 2 : (n >= p.d ? 1 : 0), nn = n - which * p.d;
+            if (which == 0) {
+                p.q32[(size_t)row * p.d + nn] = v;
+            } else {
+                const int tk = row / p.rows_real, rr = row - tk * p.rows_real;
+                __half* cache = which == 2 ? p.vc : p.kc;
+                cache[(((size_t)rr * p.H + (nn >> 6)) * p.cache_len + cache_pos + tk) * 64 + (nn & 63)] = __float2half_rn(v);
+            }
         } else {  // EPI_CROSSKV: GEMM rows are (row, text position) pairs
             const int R = p.row0 + row, r = R / p.text_len, tc = R % p.text_len;
             const int which = n / p.d, nn = n % p.d, h = nn >> 6, dd = nn & 63;
@@ -323,6 +335,7 @@ struct AttnParams {
     const __half* kc; const __half* vc; __half* out;
     int H, d, cache_len; const int* pos; int fixed_len; float scale;
     unsigned long long* timing;   // debug timeline
+    int rows_real;                // prefill (PF kernels): rows of the generation
     float* part; int* counter;    // split-KV self attention (gridDim.z > 1): partial (m, l, acc[64]) records, arrival counters
     int split_min;                // contexts shorter than this stay on the single-CTA path
 };
@@ -347,16 +360,20 @@ __device__ __forceinline__ void osm_merge(OnlineSM& a, float m2, float l2, const
     a.m = mn;
 }
 
-template <bool SPLIT>   // SPLIT = false (default step): none of the chunk / record / merge code is compiled in
+// SPLIT = false (default step): none of the chunk / record / merge code is compiled in.  PF (prompt prefill): blockIdx.y is a
+// (token, row) pair tok * rows_real + r; the query at position pos + tok attends to the cache of row r up to and including
+// its own position (the QKV GEMM of the same pass has already appended every token of the pass: causal within the chunk).
+template <bool SPLIT, bool PF = false>
 __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     __shared__ float wm[ATT_WARPS], wl[ATT_WARPS], wacc[ATT_WARPS][64];
-    const int h = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qrow = blockIdx.y, row = PF ? qrow % p.rows_real : qrow, tok = PF ? qrow / p.rows_real : 0;
     const int sl = lane & 7, pg = lane >> 3;
     tl_stamp(p.timing, 0);
     pdl_trigger();
     pdl_wait();
     tl_stamp(p.timing, 1);
-    const int n = p.fixed_len > 0 ? p.fixed_len : p.pos[0] + 1;
+    const int n = p.fixed_len > 0 ? p.fixed_len : p.pos[0] + tok + 1;
     int lo = 0, hi = n, nact = 1;
     if (SPLIT && gridDim.z > 1) {
         // measured: the record write + atomic + merge costs more than the balance gains below ~750 positions
@@ -371,7 +388,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     float q[8];
     {   // (split-K query partials exist only on the cross-attention path; a rolled/unrolled split loop here cost
         //  ~1 500 instructions of cold code per launch)
-        const float4* qp = reinterpret_cast<const float4*>(p.q + (size_t)row * p.d + h * 64 + sl * 8);
+        const float4* qp = reinterpret_cast<const float4*>(p.q + (size_t)qrow * p.d + h * 64 + sl * 8);
         const float4 qa = qp[0], qb = qp[1];
         q[0] = half_round(qa.x) * p.scale; q[1] = half_round(qa.y) * p.scale; q[2] = half_round(qa.z) * p.scale;
         q[3] = half_round(qa.w) * p.scale; q[4] = half_round(qb.x) * p.scale; q[5] = half_round(qb.y) * p.scale;
@@ -461,7 +478,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
         }
     }
     if (!SPLIT || nact == 1) {                       // CTA-uniform
-        if (tid < 64) p.out[(size_t)row * p.d + h * 64 + tid] = __float2half_rn(o / l);
+        if (tid < 64) p.out[(size_t)qrow * p.d + h * 64 + tid] = __float2half_rn(o / l);
     } else {
         __shared__ int is_last;
         float* rec = p.part + ((size_t)row * p.H + h) * gridDim.z * 66;
@@ -494,6 +511,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
 
 // Cross attention over the (short) text condition: one WARP per (row, head), lane = text position for the scores,
 // lane = 2 output dims for the weighted sum.  K/V were computed once per generate() (acb_lm_begin).
+template <bool PF>
 __global__ void __launch_bounds__(256) lm_cross_attn_kernel(AttnParams p, int rows) {
     __shared__ float qs[8][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -518,7 +536,7 @@ __global__ void __launch_bounds__(256) lm_cross_attn_kernel(AttnParams p, int ro
     }
     __syncwarp();
     tl_stamp(p.timing, 4);
-    const size_t base = ((size_t)row * p.H + h) * p.cache_len * 64;
+    const size_t base = ((size_t)(PF ? row % p.rows_real : row) * p.H + h) * p.cache_len * 64;   // K / V of the generation row
     float mx = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
     for (int t0 = 0; t0 < n; t0 += 32) {             // chunks of 32 text positions (online softmax across chunks)
         const int t = t0 + lane;
@@ -830,7 +848,7 @@ static int launch_gemm_ft(int nt, const GemmParams& p, int nsplit, cudaStream_t 
 template <int EPI>
 static int launch_gemm(int nt, const GemmParams& p, int nsplit, cudaStream_t s, bool pdl, int ft2 = 1) {
     if (ft2 == 2) {
-        if constexpr (EPI == EPI_CROSSKV) { acb_set_error("lm_gemm: the cross-K/V prefill uses 16-feature tiles"); return ACB_ERR_INVALID; }
+        if constexpr (EPI == EPI_CROSSKV || EPI == EPI_QKV_PF) { acb_set_error("lm_gemm: this epilogue uses 16-feature tiles"); return ACB_ERR_INVALID; }
         else return launch_gemm_ft<EPI, 2>(nt, p, nsplit, s, pdl);
     }
     return launch_gemm_ft<EPI, 1>(nt, p, nsplit, s, pdl);
@@ -849,7 +867,7 @@ static cudaError_t gemm_attr_all() {
     if ((e = gemm_attr_one<2, EPI, 1>()) != cudaSuccess) return e;
     if ((e = gemm_attr_one<4, EPI, 1>()) != cudaSuccess) return e;
     if ((e = gemm_attr_one<8, EPI, 1>()) != cudaSuccess) return e;
-    if constexpr (EPI != EPI_CROSSKV) {
+    if constexpr (EPI != EPI_CROSSKV && EPI != EPI_QKV_PF) {
         if ((e = gemm_attr_one<1, EPI, 2>()) != cudaSuccess) return e;
         if ((e = gemm_attr_one<2, EPI, 2>()) != cudaSuccess) return e;
         if ((e = gemm_attr_one<4, EPI, 2>()) != cudaSuccess) return e;
@@ -916,12 +934,18 @@ static int acb_dbg(cudaStream_t s, bool capturing, const char* what, int layer) 
 }
 #define DBG(what, layer) ACB_TRY(acb_dbg(s, capturing, what, layer))
 
+// pf_tokens > 0: PROMPT PREFILL pass (the multi-token first call of the reference, transformer.py:240-247, 413-414, lm.py:513-534):
+// the same kernels run on rows * pf_tokens (token, row) pairs -- positions pos .. pos + pf_tokens - 1 of every row at once, causal
+// inside the pass because the QKV GEMM appends all of them to the cache before the attention kernel runs -- and stop after the
+// last layer (no logits: the next decode step consumes the last prompt position).
 static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, int* n_launch, bool gemms_only,
-                                bool capturing) {
+                                bool capturing, int pf_tokens = 0) {
     const acb_lm_config& c = lm->cfg;
     const acb_lm_buffers& B = lm->buf;
-    const int d = c.dim, ffn = c.ffn_dim, L = c.num_layers, H = c.num_heads, rows = lm->rows, nt = nt_for_rows(rows);
-    const size_t part_stride = (size_t)lm->rows_pad * d;
+    const bool pf = pf_tokens > 0;
+    const int rows_real = lm->rows, rows = pf ? rows_real * pf_tokens : rows_real;
+    const int d = c.dim, ffn = c.ffn_dim, L = c.num_layers, H = c.num_heads, nt = nt_for_rows(rows);
+    const size_t part_stride = (size_t)(pf ? 8 * nt : lm->rows_pad) * d;
     const size_t kv_layer = (size_t)c.max_rows * H * c.max_seq * 64;
     const size_t ckv_layer = (size_t)c.max_rows * H * c.max_text * 64;
     const float scale = 1.0f / sqrtf(64.f);
@@ -929,8 +953,10 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
     int nl = 0, ks = 0;
 
     if (!gemms_only) {
-        ACB_LAUNCH(lm_embed_kernel, dim3(rows), dim3(256), 0, s, pdl, (const __half*)lm->w.emb, lm->w.inv_freq,
-                   (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale);
+        if (pf) ACB_LAUNCH(lm_embed_kernel<true>, dim3(rows), dim3(256), 0, s, pdl, (const __half*)lm->w.emb, lm->w.inv_freq,
+                           (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale, rows_real);
+        else ACB_LAUNCH(lm_embed_kernel<false>, dim3(rows), dim3(256), 0, s, pdl, (const __half*)lm->w.emb, lm->w.inv_freq,
+                        (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale, rows);
         ++nl;
         DBG("lm_embed_kernel", -1);
     }
@@ -986,10 +1012,12 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             pick_split(3 * d, d, lm->sms, false, &ks);
             GemmParams p = base_gemm((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, B.h16, 3 * d, d, rows, ks);
             p.q32 = B.q32; p.kc = (__half*)B.k_cache + l * kv_layer; p.vc = (__half*)B.v_cache + l * kv_layer;
-            p.d = d; p.H = H; p.cache_len = c.max_seq; p.pos = B.pos;
-            const int ft2 = pick_ft2(3 * d, d, 1, ks, nt, lm->sms);
+            p.d = d; p.H = H; p.cache_len = c.max_seq; p.pos = B.pos; p.rows_real = rows_real;
+            const int ft2 = pf ? 1 : pick_ft2(3 * d, d, 1, ks, nt, lm->sms);
             p.timing = tl("gemm_QKV", l, 3 * d / (16 * ft2));
-            ACB_TRY(launch_gemm<EPI_QKV>(nt, p, 1, s, pdl, ft2)); ++nl;
+            if (pf) ACB_TRY(launch_gemm<EPI_QKV_PF>(nt, p, 1, s, pdl, 1));
+            else ACB_TRY(launch_gemm<EPI_QKV>(nt, p, 1, s, pdl, ft2));
+            ++nl;
             DBG("gemm_EPI_QKV", l);
         }
         if (!gemms_only) {
@@ -999,7 +1027,9 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             a.part = reinterpret_cast<float*>((unsigned char*)B.plan + ACB_PLAN_COUNTER_BYTES);
             a.counter = reinterpret_cast<int*>(B.plan);
             a.split_min = max(129, env_int("ACB_LM_ATT_SPLIT_MIN", 768));
-            if (att_split > 1) ACB_LAUNCH(lm_attn_kernel<true>, dim3(H, rows, att_split), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            a.rows_real = rows_real;
+            if (pf) ACB_LAUNCH((lm_attn_kernel<false, true>), dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            else if (att_split > 1) ACB_LAUNCH(lm_attn_kernel<true>, dim3(H, rows, att_split), dim3(ATT_WARPS * 32), 0, s, pdl, a);
             else ACB_LAUNCH(lm_attn_kernel<false>, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
             ++nl;
             DBG("lm_attn_kernel", l);
@@ -1016,7 +1046,9 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
                              (__half*)B.cv_cache + l * ckv_layer, (__half*)B.a16, H, d, c.max_text, B.pos, lm->text_len,
                              scale};
                 a.timing = tl("cross_attn", l, acb_ceil_div(rows * H, 8));
-                ACB_LAUNCH(lm_cross_attn_kernel, dim3(acb_ceil_div(rows * H, 8)), dim3(256), 0, s, pdl, a, rows);
+                a.rows_real = rows_real;
+                if (pf) ACB_LAUNCH(lm_cross_attn_kernel<true>, dim3(acb_ceil_div(rows * H, 8)), dim3(256), 0, s, pdl, a, rows);
+                else ACB_LAUNCH(lm_cross_attn_kernel<false>, dim3(acb_ceil_div(rows * H, 8)), dim3(256), 0, s, pdl, a, rows);
                 ++nl;
                 DBG("lm_cross_attn_kernel", l);
             }
@@ -1034,6 +1066,10 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             DBG("gemm_EPI_GELU", l);
         }
         ACB_TRY(partial_gemm((const __half*)lm->w.w_ff2 + (size_t)l * d * ffn, B.f16, d, ffn, l, G_FF2));
+    }
+    if (pf) {   // no output norm / heads / sampler: the pass only fills the KV cache
+        if (n_launch) *n_launch = nl;
+        return ACB_OK;
     }
     ACB_TRY(ln_launch(lm->w.out_norm, lm->w.out_norm + d, -1));
     {
@@ -1113,11 +1149,12 @@ extern "C" int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, 
     if (ea == cudaSuccess) ea = gemm_attr_all<EPI_GELU>();
     if (ea == cudaSuccess) ea = gemm_attr_all<EPI_F32>();
     if (ea == cudaSuccess) ea = gemm_attr_all<EPI_CROSSKV>();
+    if (ea == cudaSuccess) ea = gemm_attr_all<EPI_QKV_PF>();
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_cross_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_cross_attn_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_ln_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_embed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_embed_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_sample_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea != cudaSuccess) {
         acb_set_error("acb_lm_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ea));
@@ -1244,6 +1281,44 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
             return rc != ACB_OK ? rc : ACB_ERR_CUDA;
         }
         lm->pdl = false;   // retry without programmatic edges
+    }
+    return ACB_OK;
+}
+
+__global__ void lm_set_pos_kernel(int* pos, int value) { pos[0] = value; }
+
+// Prompt prefill: consume sequence positions [pos0, pos0 + n_tokens) of every row (their tokens are already in buffers.seq)
+// without sampling, ACB_LM_PREFILL_ROWS / rows positions per pass.  Leaves pos = pos0 + n_tokens on the device.
+extern "C" int acb_lm_prefill(acb_lm_t* lm, int pos0, int n_tokens, void* stream) {
+    ACB_REQUIRE(lm && lm->rows > 0, "acb_lm_prefill: call acb_lm_begin first");
+    ACB_REQUIRE(!lm->fused, "acb_lm_prefill: the prefill pass is built on the per-phase kernels");
+    ACB_REQUIRE(pos0 >= 0 && n_tokens >= 0 && pos0 + n_tokens < lm->seq_len, "acb_lm_prefill: positions [%d, %d) exceed the sequence (%d)",
+                pos0, pos0 + n_tokens, lm->seq_len);
+    cudaStream_t s = (cudaStream_t)stream;
+    const acb_lm_config& c = lm->cfg;
+    const int d = c.dim, per = ACB_LM_PREFILL_ROWS / lm->rows;
+    ACB_REQUIRE(per >= 1, "acb_lm_prefill: rows %d > %d", lm->rows, ACB_LM_PREFILL_ROWS);
+    int done = 0;
+    while (done < n_tokens) {
+        const int tc = n_tokens - done < per ? n_tokens - done : per;
+        const int vrows = lm->rows * tc, pad = 8 * nt_for_rows(vrows);
+        lm_set_pos_kernel<<<1, 1, 0, s>>>(lm->buf.pos, pos0 + done);
+        ACB_LAUNCH_CHECK();
+        if (pad > vrows) {   // the GEMMs read their activation rows up to the tile height: rows >= vrows must be zero
+            ACB_CHECK_CUDA(cudaMemsetAsync((__half*)lm->buf.h16 + (size_t)vrows * d, 0, (size_t)(pad - vrows) * d * sizeof(__half), s));
+            ACB_CHECK_CUDA(cudaMemsetAsync((__half*)lm->buf.a16 + (size_t)vrows * d, 0, (size_t)(pad - vrows) * d * sizeof(__half), s));
+            ACB_CHECK_CUDA(cudaMemsetAsync((__half*)lm->buf.f16 + (size_t)vrows * c.ffn_dim, 0, (size_t)(pad - vrows) * c.ffn_dim * sizeof(__half), s));
+        }
+        ACB_TRY(enqueue_step_kernels(lm, s, nullptr, nullptr, false, false, tc));
+        done += tc;
+    }
+    lm_set_pos_kernel<<<1, 1, 0, s>>>(lm->buf.pos, pos0 + n_tokens);
+    ACB_LAUNCH_CHECK();
+    // back to decode: its padded rows [rows, rows_pad) must be zero again
+    if (lm->rows_pad > lm->rows) {
+        ACB_CHECK_CUDA(cudaMemsetAsync((__half*)lm->buf.h16 + (size_t)lm->rows * d, 0, (size_t)(lm->rows_pad - lm->rows) * d * sizeof(__half), s));
+        ACB_CHECK_CUDA(cudaMemsetAsync((__half*)lm->buf.a16 + (size_t)lm->rows * d, 0, (size_t)(lm->rows_pad - lm->rows) * d * sizeof(__half), s));
+        ACB_CHECK_CUDA(cudaMemsetAsync((__half*)lm->buf.f16 + (size_t)lm->rows * c.ffn_dim, 0, (size_t)(lm->rows_pad - lm->rows) * c.ffn_dim * sizeof(__half), s));
     }
     return ACB_OK;
 }

@@ -138,16 +138,21 @@ class EncodecModel(CompressionModel):
     """EnCodec (SEANet + RVQ) on B200 behind the reference's ``EncodecModel`` API."""
 
     def __init__(self, state_dict: tp.Dict[str, torch.Tensor], cfg: dict, device='cuda',
-                 encoder_precision: str = 'fp32', decoder_precision: str = 'tf32x3'):
-        """encoder_precision / decoder_precision: 'fp32' (FMA) or 'tf32x3' (tensor pipe, split operands).  The encoder
-        defaults to fp32 so that RVQ indices equal the fp32 reference's; the decoder's output is a waveform checked to a
-        tolerance (1e-4) and defaults to the faster 3xTF32 convolutions."""
+                 encoder_precision: str = 'fp32_tc', decoder_precision: str = 'tf32x3'):
+        """encoder_precision / decoder_precision:
+          'fp32'         every convolution on fp32 FMA;
+          'fp32_tc'      (encoder default) fp32 ACCURACY on the tensor cores: layers with kernel > 1 and >= 128 output channels
+                         run `acb_conv1d_t6` (tcgen05, 3xTF32 operand split, the TMEM accumulator flushed into fp32 registers
+                         every 8 input channels), the rest fp32 FMA.  Latents within 3.0e-6 of the fp32 reference on the 24 /
+                         32 kHz architectures (all-FMA: 3.6e-6), RVQ indices exact (profiles/r2_t6_first_hardware_contact_*.log);
+          'tf32x3_flush' the same kernel on every layer it supports (slower on 1x1 convolutions; kept for tests);
+          'tf32x3'       (decoder default, NOT fp32-exact) tcgen05 3xTF32 without flushes: the decoder's output is a waveform
+                         checked to a tolerance of 1e-4; as an encoder mode its latents move by 1.5e-4."""
         self.device = _lib.require_cuda(device)
-        # ('tf32x3_flush' is EXPERIMENTAL and not validated on hardware yet: implicit-GEMM tcgen05 convs with fp32 flushes)
         prec = {'fp32': _lib.CONV_FP32, 'tf32x3': _lib.CONV_TF32X3, 'tf32x3_mmasync': _lib.CONV_TF32X3_MMASYNC,
-                'tf32x3_flush': _lib.CONV_T6_FLUSH}
+                'tf32x3_flush': _lib.CONV_T6_FLUSH, 'fp32_tc': _lib.CONV_T6_AUTO}
         self._enc_prec, self._dec_prec = prec[encoder_precision], prec[decoder_precision]
-        self._want_t6 = _lib.CONV_T6_FLUSH in (self._enc_prec, self._dec_prec)
+        self._want_t6 = bool({_lib.CONV_T6_FLUSH, _lib.CONV_T6_AUTO} & {self._enc_prec, self._dec_prec})
         # the LSTM input projections (one 1x1 conv per layer) always run on the tensor cores: measured 3.9e-6 vs 3.6e-6 latent
         # error for the otherwise-fp32 encoder (the tensor-core error of the conv stack comes from its long reductions)
         self._lstm_prec = _lib.CONV_TF32X3
@@ -226,6 +231,10 @@ class EncodecModel(CompressionModel):
         cout = L['cout'] if cout is None else cout
         left, t_virt, t_out = conv_geometry(T, k, stride, dilation, self.causal, bool(self.reflect))
         y = torch.empty((B, cout, t_out), device=x.device, dtype=torch.float32)
+        if prec == _lib.CONV_T6_AUTO:
+            # measured per layer on 32 x 10 s (profiles/r2_perf_encodec_t6_all_layers.log vs r1_perf_encodec_v5_t5pipelined.log):
+            # the implicit-GEMM tcgen05 kernel wins for k > 1 with >= 128 output channels (1.5-4x), loses on 1x1 convolutions
+            prec = _lib.CONV_T6_FLUSH if (k > 1 and cout >= 128) else _lib.CONV_FP32
         if prec == _lib.CONV_T6_FLUSH:
             if w is None and 'w6' in L and cout == L['cout']:
                 _lib.check(self._lib.acb_conv1d_t6(_lib.ptr(x), _lib.ptr(L['w6']), _lib.ptr(L['b'] if b is None else b),
@@ -246,7 +255,7 @@ class EncodecModel(CompressionModel):
         B, cin, T = x.shape
         trim_left, t_out = convtr_geometry(T, L['k'], L['stride'], self.causal, self.cfg['trim_right_ratio'])
         y = torch.empty((B, L['cout'], t_out), device=x.device, dtype=torch.float32)
-        if prec == _lib.CONV_T6_FLUSH:
+        if prec in (_lib.CONV_T6_FLUSH, _lib.CONV_T6_AUTO):
             prec = _lib.CONV_TF32X3        # transposed convs have no implicit-GEMM variant yet
         _lib.check(self._lib.acb_convtr1d(_lib.ptr(x), _lib.ptr(L['w']), _lib.ptr(L['w_gemm']), _lib.ptr(L['b']),
                                           _lib.ptr(y), B, cin, L['cout'], T, t_out, L['k'], L['stride'], trim_left,

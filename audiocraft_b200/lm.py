@@ -164,7 +164,8 @@ class LMModel:
         max_seq = seq_len if shape is None else max(seq_len, shape[1])
         max_text = max(1, text_len if shape is None else max(text_len, shape[2]))
         max_batch = batch if shape is None else max(batch, shape[3])
-        rp = self._lib.acb_lm_rows_pad(max_rows)
+        # activation buffers also hold the (token, row) pairs of a prompt-prefill pass (acb_lm_prefill)
+        rp = max(self._lib.acb_lm_rows_pad(max_rows), _lib.ACB_LM_PREFILL_ROWS)
         f16, f32 = torch.float16, torch.float32
         b = {}
         b['x'] = torch.zeros((rp, d), device=dev, dtype=f32)
@@ -218,6 +219,11 @@ class LMModel:
             self._destroy()
         except Exception:
             pass
+
+    def _fused_active(self) -> bool:
+        import os as _os
+        return self._w.get('wp_qkv') is not None and (_os.environ.get('ACB_LM_STEP', '').startswith('f')
+                                                      or self.positional_embedding != 'sin')
 
     # ------------------------------------------------------------------ conditions (lm.py:488-511)
     def _prepare_conditions(self, conditions, two_step_cfg, cfg_coef_beta):
@@ -307,10 +313,19 @@ class LMModel:
                                               _lib.stream()), 'lm_begin')
             self.launches_per_step = self._lib.acb_lm_launches_per_step(self._handle)
             n_steps = S - 1
+            # Prompt prefill (the reference's multi-token first call, lm.py:513-534, transformer.py:240-247): positions
+            # [0, start - 1) only feed the KV cache -- their tokens are known and the first sampled position is `start` -- so
+            # they go through acb_lm_prefill, several positions per pass, instead of one decode step each.
+            first = 0
+            import os as _os
+            if (start_offset_sequence - 1 >= 2 and rows <= _lib.ACB_LM_PREFILL_ROWS and not self._fused_active()
+                    and _os.environ.get('ACB_LM_PREFILL', '1') != '0'):
+                first = start_offset_sequence - 1
+                _lib.check(self._lib.acb_lm_prefill(self._handle, 0, first, _lib.stream()), 'lm_prefill')
             if callback is None and self._debug_noise_fn is None:
-                _lib.check(self._lib.acb_lm_steps(self._handle, n_steps, _lib.stream()), 'lm_steps')
+                _lib.check(self._lib.acb_lm_steps(self._handle, n_steps - first, _lib.stream()), 'lm_steps')
             else:
-                for pos in range(n_steps):
+                for pos in range(first, n_steps):
                     offset = pos + 1
                     if self._debug_noise_fn is not None:
                         bufs['noise'][:B].copy_(self._debug_noise_fn(offset, (B, K, self.card)).reshape(B, K, self.card))

@@ -2,7 +2,14 @@
 configuration the headline metric `audio-sec/sec` is quoted on; it fits one B200.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--duration 30] [--batch 8]
+                  [--scaling weak|strong] [--scale small|medium|large] [--workload musicgen|encodec]
   torchrun --nproc-per-node N bench.py --gpus N ...
+
+Defaults = BASELINE configs[2] with `--batch` items PER GPU (`scaling: weak`, as the contract prescribes for a path that shards
+by independent items).  `--scaling strong` splits `--batch` items over the ranks instead (configs[2] read literally: batch 8 over
+1-8 GPUs = 8/4/2/1 items per GPU) and gathers the waveforms with NCCL inside the timed region.  `--scale large --batch 32
+--scaling strong` is configs[4]; `--workload encodec --batch 256 --scaling strong` is configs[3] (EnCodec 32 kHz encode+decode
+throughput, its own metric / roofline / CPU baseline).
 
 One "step" = one full pass of the hot path over one batch: LMModel.generate (T+3 decode steps, CFG rows = 2B) followed
 by EnCodec decode of the tokens to audio.  `value` = audio seconds produced by all ranks / max-over-ranks device time,
@@ -106,6 +113,116 @@ def dist_setup(n):
     return rank, world
 
 
+def encodec_roofline(samples: int, ms: float):
+    """SURVEY.md section 8d for EnCodec-32k encode+decode: 4 822 B/sample when every layer reads its input and writes its
+    output once (fp32, ELU / residual / padding fused) and 486 kFLOP/sample.  With tensor-core convolutions the per-layer design
+    is HBM-bound (101 FLOP/B < the ridge), so the HBM figure is the binding one; the tensor figure is reported beside it."""
+    pj = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
+    hbm = pj.get('hbm_gbs', 6650.0)
+    tf = pj.get('bf16_tflops_sustained', 1400.0)
+    gbs = samples * 4822 / (ms / 1e3) / 1e9
+    tfl = samples * 486e3 / (ms / 1e3) / 1e12
+    return dict(bound='hbm', achieved=round(gbs, 1), peak=hbm, unit='GB/s', frac=round(gbs / hbm, 4), traffic=None,
+                algorithmic_bytes_per_sample=4822, peak_source='measured (MEASURED_PEAKS.json)' if pj else 'fallback (B200_PROFILING.md)',
+                tensor=dict(achieved=round(tfl, 2), peak=tf, unit='TFLOP/s (fp32-equivalent work vs the measured dense bf16 peak)',
+                            frac=round(tfl / tf, 4), flop_per_sample=486000))
+
+
+def run_encodec(args):
+    """BASELINE configs[3]: EnCodec 32 kHz, 4 codebooks, `--batch` x 10 s encode + decode, items split over the ranks
+    (`--scaling strong`, 256 items -> 32 per GPU on 8) or `--batch` items per rank (weak)."""
+    rank, world = dist_setup(args.gpus)
+    assert torch.cuda.is_available(), "bench.py (impl b200) needs a CUDA device; there is no CPU fallback"
+    dev = torch.device('cuda', torch.cuda.current_device())
+    from audiocraft_b200.loaders import load_compression_model
+    from audiocraft_b200.dist import shard_bounds
+    strong = args.scaling == 'strong'
+    if strong:
+        a_, b_ = shard_bounds(args.batch, rank, world)
+        B = b_ - a_
+    else:
+        B = args.batch
+    total_items = args.batch if strong else args.batch * world
+    n_samp = int(10.0 * 32000)
+    cm = load_compression_model('synthetic/encodec_32k', dev, seed=1)
+    g = torch.Generator().manual_seed(7 + rank)
+    x_host = (torch.randn(B, 1, n_samp, generator=g) * 0.1).pin_memory()
+    x_dev = x_host.to(dev)
+    CH = 32                                           # items per launch chain: bounds the activation memory ([32, 64, 320000] fp32 = 2.6 GB per layer)
+
+    def step_device():
+        outs = []
+        for i in range(0, B, CH):
+            codes, scale = cm.encode(x_dev[i:i + CH])
+            outs.append(cm.decode(codes, scale))
+        return outs
+
+    def step_e2e():
+        y = torch.empty((B, 1, n_samp), dtype=torch.float32, pin_memory=True)
+        for i in range(0, B, CH):
+            xb = x_host[i:i + CH].to(dev, non_blocking=True)
+            codes, scale = cm.encode(xb)
+            w = cm.decode(codes, scale)
+            y[i:i + CH].copy_(w[..., :n_samp], non_blocking=True)
+        return y
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def timed(fn, n):
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, out
+
+    for _ in range(args.warmup):
+        l0 = cm.launches
+        step_device()
+        launches = cm.launches - l0
+    with ClockSampler(torch.cuda.current_device()) as clk:
+        ms, _ = timed(step_device, args.steps)
+    clocks = clk.summary()
+    ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 3)))
+    n_e2e = max(1, min(args.steps, 3))
+    samples_step = total_items * n_samp
+    value = samples_step * args.steps / (ms / 1e3) / 1e6
+    cpu_baseline = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+        from baseline import reference_arm as RA
+        if RA.available():
+            cpu_baseline = RA.cpu_encodec_baseline(1, 10.0)
+    if rank == 0:
+        emit(dict(metric='EnCodec 32kHz encode+decode MSamples/sec', value=round(value, 2), unit='MSamples/s', n_gpus=world,
+                  steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 2), higher_is_better=True,
+                  scaling=args.scaling, vs_baseline=None, dtype='f32', data='synthetic',
+                  config=dict(workload=f'EnCodec 32 kHz, 4 codebooks: encode + decode of {total_items} x 10 s mono, {B} items on this rank '
+                                       f'(launch chains of {CH} items); encoder fp32-accurate (index-exact), decoder 3xTF32 on tcgen05',
+                              global_batch=total_items, seq_len=n_samp, parallelism=f'dp{world} (items split, no collective)',
+                              l2=f'inputs larger than L2: every layer of a {CH}-item chain reads / writes 0.3-2.6 GB'),
+                  clocks=clocks,
+                  e2e=dict(value=round(samples_step * n_e2e / (ms_e2e / 1e3) / 1e6, 2), unit='MSamples/s',
+                           h2d_bytes_per_step=B * n_samp * 4, d2h_bytes_per_step=B * n_samp * 4),
+                  gpu_launches=launches * args.steps,
+                  roofline=encodec_roofline(B * n_samp, ms / args.steps), cpu_baseline=cpu_baseline))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def algorithmic_bytes(lm, rows, S):
     """per decode step W_step + rows*t*kv_tok (read) + rows*kv_tok (write), fp16."""
     kv_tok = 2 * lm.dim * 2 * lm.num_layers
@@ -124,7 +241,16 @@ def run_b200(args):
     from audiocraft_b200.loaders import load_musicgen
     import ctypes as C
     torch.manual_seed(1234 + rank)
-    B, dur = args.batch, args.duration
+    strong = args.scaling == 'strong'
+    if strong:
+        from audiocraft_b200.dist import shard_bounds
+        lo_, hi_ = shard_bounds(args.batch, rank, world)
+        B = hi_ - lo_
+        assert B >= 1, f'--scaling strong: batch {args.batch} < {world} ranks'
+    else:
+        B = args.batch
+    dur = args.duration
+    total_items = args.batch if strong else args.batch * world
     mg = load_musicgen(f'synthetic/{args.scale}', device=dev, seed=0)
     mg.set_generation_params(duration=dur, use_sampling=True, top_k=250, temperature=1.0, cfg_coef=3.0)
     lm, cm = mg.lm, mg.compression_model
@@ -135,24 +261,36 @@ def run_b200(args):
     from audiocraft_b200.conditioners import ConditioningAttributes
     attrs = [ConditioningAttributes(text={'description': d}) for d in descriptions]
     cross = lm._prepare_conditions(attrs, False, None).contiguous()
-    # host inputs for `e2e`: the text-encoder hidden states, pinned
-    enc = lm.condition_provider.conditioners['description'].encoder
-    hid, msk = enc(descriptions + [""] * B)
-    hid_pinned, msk_pinned = hid.pin_memory(), msk.pin_memory()
+    # host inputs for `e2e`: the text-encoder hidden states live in PINNED host memory and are handed to the public call
+    # MusicGen.generate(descriptions) by the conditioner's encoder hook (the frozen T5 is outside the hot path): the H2D copy
+    # happens inside generate(), in the timed region, and the waveform is read back to the host.
+    cond_mod = lm.condition_provider.conditioners['description']
+    synth_enc = cond_mod.encoder
+    table = {}
+    for dsc in descriptions + [""]:
+        h_, m_ = synth_enc([dsc])
+        table[dsc] = (h_[0].pin_memory(), m_[0].pin_memory())
+
+    def pinned_encoder(entries):
+        return torch.stack([table[e][0] for e in entries]).pin_memory(), torch.stack([table[e][1] for e in entries]).pin_memory()
+
+    hid, msk = pinned_encoder(descriptions + [""] * B)
     h2d_bytes = hid.numel() * 4 + msk.numel() * 8
 
     def step_device():
         tokens = lm.generate(None, [], num_samples=B, max_gen_len=T, cross_attention_src=cross, **mg.generation_params)
-        return mg.generate_audio(tokens)
+        wav = mg.generate_audio(tokens)
+        if strong and world > 1:   # configs[2] read literally: one batch over the ranks, the audio gathered on every rank
+            from audiocraft_b200.dist import gather_batch
+            wav = gather_batch(wav, args.batch)
+        return wav
 
     def step_e2e():
-        # what MusicGen.generate(descriptions) does, with the encoder states coming from pinned host memory
-        h = hid_pinned.to(dev, non_blocking=True)
-        m_ = msk_pinned.to(dev, non_blocking=True)
-        m_[B:] = 0
-        cond = lm.condition_provider.conditioners['description']({'hidden': h, 'attention_mask': m_})[0]
-        tokens = lm.generate(None, [], num_samples=B, max_gen_len=T, cross_attention_src=cond, **mg.generation_params)
-        wav = mg.generate_audio(tokens)
+        cond_mod.encoder = pinned_encoder
+        try:
+            wav = mg.generate(descriptions)            # the public API call (genmodel.py:151-171)
+        finally:
+            cond_mod.encoder = synth_enc
         return wav.to('cpu', non_blocking=False)
 
     def barrier():
@@ -187,10 +325,11 @@ def run_b200(args):
     with ClockSampler(torch.cuda.current_device()) as clk:
         ms, wav = timed(step_device, args.steps)
     clocks = clk.summary()
-    audio_s = B * dur * world * args.steps
+    audio_s = total_items * dur * args.steps
     value = audio_s / (ms / 1e3)
-    ms_e2e, wav_host = timed(step_e2e, max(1, min(args.steps, 2)))
-    e2e_value = B * dur * world * max(1, min(args.steps, 2)) / (ms_e2e / 1e3)
+    n_e2e = max(1, min(args.steps, 3))
+    ms_e2e, wav_host = timed(step_e2e, n_e2e)
+    e2e_value = total_items * dur * n_e2e / (ms_e2e / 1e3)
     d2h_bytes = wav_host.numel() * 4
 
     # ---- dominant kernel, timed in isolation with CUDA events on the launching stream (acb_lm_debug_gemms enqueues only it).
@@ -268,8 +407,8 @@ def run_b200(args):
         torch.cuda.synchronize()
         enc_ms = e0.elapsed_time(e1) / 3
         secondary = dict(metric='EnCodec 32kHz encode+decode MSamples/sec', value=round(xb.numel() / (enc_ms / 1e3) / 1e6, 2),
-                         unit='MSamples/s', config='32 x 10 s mono per GPU; encoder fp32 FMA (index-exact), decoder 3xTF32 on tcgen05',
-                         ms=round(enc_ms, 2))
+                         unit='MSamples/s', config='32 x 10 s mono per GPU; encoder fp32-accurate (tcgen05 3xTF32 with fp32 flushes where it wins, fp32 FMA elsewhere: index-exact), decoder 3xTF32 on tcgen05',
+                         ms=round(enc_ms, 2), roofline=encodec_roofline(xb.numel(), enc_ms))
         # throughput mode: the encoder's convolutions on the tensor cores as well (latents within 1.5e-4 of fp32)
         from audiocraft_b200 import synth as _synth
         from audiocraft_b200.encodec import EncodecModel as _EM
@@ -311,11 +450,15 @@ def run_b200(args):
 
     if rank == 0:
         line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling='weak', vs_baseline=None,
+                    ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                     dtype='f16', data='synthetic',
                     config=dict(workload=f'MusicGen-{args.scale} text-conditioned {dur:g}s generation, batch={B} per GPU '
                                          f'(CFG rows={2 * B}), top_k=250, EnCodec-32k decode included',
-                                global_batch=B * world, seq_len=T, parallelism=f'dp{world} (batch split, no collective)',
+                                global_batch=total_items, seq_len=T,
+                                parallelism=(f'dp{world}: one batch of {args.batch} split over the ranks, waveforms all-gathered (NCCL) in the timed region'
+                                             if strong else f'dp{world} (batch split, no collective)'),
+                                limiter=('per-replica weight stream: every rank re-reads the %.2f GB of weights per decode step at the same '
+                                         'latency-bound step time whatever its share of the batch' % (w_step / 1e9)) if strong else None,
                                 pdl=bool(lm._lib.acb_lm_uses_pdl(lm._handle)),
                                 l2='inputs larger than L2: every decode step streams %.2f GB of weights' % (w_step / 1e9)),
                     clocks=clocks,
@@ -396,11 +539,15 @@ if __name__ == '__main__':
     ap.add_argument('--duration', type=float, default=30.0)
     ap.add_argument('--batch', type=int, default=8)
     ap.add_argument('--cpu-steps', type=int, default=4, help='decode steps per KV window of one CPU reference sample')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--workload', default='musicgen', choices=['musicgen', 'encodec'])
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-ref-gpu', action='store_true', help='skip timing the reference CUDA path (reference_gpu block)')
     ap.add_argument('--no-encodec', action='store_true')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.workload == 'encodec':
+        run_encodec(a)
     else:
         run_b200(a)

@@ -186,6 +186,7 @@ typedef struct {
 
 #define ACB_LM_MAX_SPLIT 8
 #define ACB_LM_PART_SLOTS 16
+#define ACB_LM_PREFILL_ROWS 64   /* (token, row) pairs one prefill pass handles = the tallest GEMM tile */
 #define ACB_LM_PLAN_BYTES (2u << 20)
 
 typedef struct {
@@ -219,6 +220,13 @@ int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int rows, int text
  * (_sample_next_token lm.py:393-418), apply the pattern mask and write seq[:,:,offset] where it is still -1.
  * Each step is one CUDA-graph launch; nothing returns to the host. */
 int acb_lm_steps(acb_lm_t* lm, int n_steps, void* stream);
+
+/* Prompt prefill = the reference's multi-token first call (modules/transformer.py:240-247, 413-414; models/lm.py:513-534):
+ * consume sequence positions [pos0, pos0 + n_tokens) of every row -- their tokens are already in buffers.seq -- without
+ * sampling, ACB_LM_PREFILL_ROWS / rows positions per pass (the per-phase kernels on (token, row) pairs, causal inside a pass),
+ * and leave the device position at pos0 + n_tokens.  The activation buffers must hold ACB_LM_PREFILL_ROWS rows.
+ * Per-phase path only (not with ACB_LM_STEP=fused). */
+int acb_lm_prefill(acb_lm_t* lm, int pos0, int n_tokens, void* stream);
 
 /* Teacher-forced / inspection variant of one step: same as acb_lm_steps(1) and additionally leaves the
  * CFG-mixed logits [batch][n_q][card] fp32 in logits_out (may be NULL). */

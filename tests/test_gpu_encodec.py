@@ -52,9 +52,6 @@ def test_conv1d_matches_oracle(cin, cout, k, s, d, causal, L):
         torch.testing.assert_close(y.cpu(), ref, rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.skipif(os.environ.get('ACB_TEST_EXPERIMENTAL') != '1',
-                    reason='conv1d_t6 was written after the round-1 GPU budget was spent: not validated on hardware yet '
-                           '(its layout arithmetic is pinned on CPU by tests/test_t6_layout.py); set ACB_TEST_EXPERIMENTAL=1')
 @pytest.mark.parametrize('cin,cout,k,s,d,causal,L', [
     (64, 128, 8, 4, 1, False, 1001), (128, 64, 3, 1, 1, False, 333), (8, 64, 7, 1, 1, False, 500), (16, 128, 10, 5, 1, False, 2003),
     (64, 256, 16, 8, 1, True, 4100), (8, 64, 3, 1, 2, False, 77), (8, 64, 7, 1, 1, False, 3), (512, 1024, 16, 8, 1, False, 4000),
@@ -295,7 +292,6 @@ def test_tensor_core_encoder_mode(name):
     assert (codes.cpu() == g['codes']).float().mean() > 0.98
 
 
-@pytest.mark.skipif(os.environ.get('ACB_TEST_EXPERIMENTAL') != '1', reason='conv1d_t6 not validated on hardware yet (round 2)')
 @pytest.mark.parametrize('name', ['encodec_32k', 'encodec_24k'])
 def test_experimental_flush_encoder_mode(name):
     """encoder_precision='tf32x3_flush': the implicit-GEMM tcgen05 convs with per-8-channel fp32 flushes are meant to make

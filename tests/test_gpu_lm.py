@@ -419,3 +419,28 @@ def test_fused_step_matches_per_phase_kernels(monkeypatch, name, B):
     print(f'{name} B={B}: max |fused - per-phase| = {(fused - base).abs().max():.2e} on |logits| <= {base.abs().max():.1f}')
     torch.testing.assert_close(fused, base, rtol=0, atol=4e-2)
     assert (out_f == out_b).float().mean() > 0.9
+
+
+@pytest.mark.parametrize('name,B,T0', [('lm_mini', 2, 9), ('lm_mini', 5, 23), ('lm_medium_2l', 8, 21)])
+def test_prompt_prefill_equals_token_by_token(monkeypatch, name, B, T0):
+    """Prompt prefill (acb_lm_prefill = the reference's multi-token first call, lm.py:513-534, transformer.py:240-247): 64 / rows
+    prompt positions per pass through the per-phase kernels on (token, row) pairs, causal inside the pass.  Must leave the same
+    KV cache as feeding the prompt one decode step at a time and continue with the same greedy tokens (streaming == batch,
+    tests/modules/test_transformer.py:71-85)."""
+    cfg, sd, m = _model(name, 5)
+    T = T0 + 6
+    _, _, cross = H.lm_condition(cfg, sd, B, 5, 1)
+    prompt = torch.randint(0, cfg['card'], (B, 4, T0), generator=torch.Generator().manual_seed(3))
+    out_pf = m.generate(prompt.cuda(), [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross).cpu()
+    kc_pf = m._bufs['k_cache'][:, :2 * B, :, :T0].clone()
+    vc_pf = m._bufs['v_cache'][:, :2 * B, :, :T0].clone()
+    monkeypatch.setenv('ACB_LM_PREFILL', '0')
+    out_ss = m.generate(prompt.cuda(), [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross).cpu()
+    kc_ss = m._bufs['k_cache'][:, :2 * B, :, :T0]
+    vc_ss = m._bufs['v_cache'][:, :2 * B, :, :T0]
+    print(f'{name} B={B} T0={T0}: max |K cache diff| {(kc_pf.float() - kc_ss.float()).abs().max():.2e}, '
+          f'|V| {(vc_pf.float() - vc_ss.float()).abs().max():.2e}, token agreement {(out_pf == out_ss).float().mean():.4f}')
+    torch.testing.assert_close(kc_pf.float(), kc_ss.float(), rtol=0, atol=4e-3)
+    torch.testing.assert_close(vc_pf.float(), vc_ss.float(), rtol=0, atol=4e-3)
+    assert torch.equal(out_pf[..., :T0], prompt)
+    assert (out_pf == out_ss).float().mean() > 0.95
