@@ -321,10 +321,11 @@ __device__ __forceinline__ uint64_t t5_desc(uint32_t smem_addr, uint32_t lbo_byt
 }
 // The same descriptor for the 128-byte-swizzled K-major layout (layout_type 2, SBO = 1024 B between 8-row groups, LBO unused):
 // a tile row is 32 fp32 = 128 contiguous bytes and its 16-byte chunk c sits at position c ^ (row & 7); tiles are 1024-byte
-// aligned and a K step of 8 tf32 advances the start address by 32 bytes.  The tensor core fetches un-swizzled (INTERLEAVE)
-// operands 16 bytes per cycle -- measured on the LM step kernel, ~300 cycles per 128x16x16 MMA -- so conv1d_t5 stages its
-// im2col and weight tiles in this layout (conv1d_t6 keeps INTERLEAVE: its taps are descriptor start-address shifts by whole
-// rows, which a swizzled layout would need base-offset arithmetic for).
+// aligned and a K step of 8 tf32 advances the start address by 32 bytes.  conv1d_t5 stages its im2col and weight tiles in this
+// layout (conflict-free 16-byte stores, and what a tensor-map TMA load would produce).  Measured: NO speed difference against the
+// INTERLEAVE layout it used in round 1 (decode 60.3 vs 60.2 ms, profiles/r2_perf_encodec_v1_fp32tc_encoder.log): the kernel
+// is bound by building its tiles, not by the tensor core's operand fetch.  conv1d_t6 keeps INTERLEAVE: its taps are descriptor
+// start-address shifts by whole rows, which a swizzled layout would need base-offset arithmetic for.
 __device__ __forceinline__ uint64_t t5_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);

@@ -94,8 +94,10 @@ __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(CT
 // 1024-byte atom the 16-byte chunk c of row r sits at chunk position c ^ (r & 7) (address bits [4,7) ^= bits [7,10), which is
 // why tiles are 1024-byte aligned).  A K step of 16 elements advances the start address by 32 bytes.
 //   start [0,14) >> 4, LBO [16,30) (ignored for swizzled K-major, 1), SBO [32,46) >> 4, version [46,48) = 1, layout [61,64) = 2
-// (The first version of this kernel used the un-swizzled INTERLEAVE layout of conv1d_t5_kernel: correct, but the tensor core
-//  then fetches its operands 16 bytes per cycle -- ~280 cycles per 128x16x16 MMA, profiles/r2_step_trace_v3_noswizzle.log.)
+// (The first version of this kernel used the un-swizzled INTERLEAVE layout of conv1d_t5_kernel.  Both layouts give the same
+//  results AND the same timing here -- profiles/r2_step_fused_v3_* vs v4_swizzle128: the ~300 cycles per MMA seen then were the
+//  accumulate dependency and the issue path, see below -- so the swizzled form is kept only because it is the layout a
+//  tensor-map TMA load would produce.)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
@@ -319,7 +321,9 @@ __device__ __forceinline__ void gemm_phase(Env& e, int gi, int layer, const floa
         if (tr) stamp(p.trace + 1024 + 8 * e.nbar + 2);
         // ---- MMAs.  Back-to-back MMAs into ONE accumulator serialise on the accumulate dependency: at N = R = 16 an MMA is
         //      ~8 cycles of math behind ~300 cycles of pipeline latency (measured: 0.15-0.19 us per MMA whatever the operand
-        //      layout, profiles/r2_step_trace_v4_swizzled.log).  The K steps therefore rotate over NACC independent TMEM
+        //      layout, profiles/r2_step_fused_v4_swizzle128_trace_kv1.log; with 4 chains the accumulators are ready 0.12 us
+        //      after the last issue instead of 0.9 us).  What remains, ~65 ns per MMA = 0.25 us per 64-K block, is the tensor
+        //      core's rate for a 128-row A operand read from shared memory at N = 16 (profiles/r2_step_fused_v7_per_kblock_stamps.log).  The K steps therefore rotate over NACC independent TMEM
         //      accumulators (columns [a R, (a+1) R)); the epilogue adds them in a fixed order.
         if (warp == ISSUE_WARP) {
             // The whole warp runs the issue loop convergently, so every operand of tcgen05.mma (descriptors, TMEM address,
