@@ -34,7 +34,7 @@ class LMWeights(C.Structure):
 class LMBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('x', 'h16', 'a16', 'f16', 'q32', 'part', 'logits', 'k_cache', 'v_cache',
                                            'ck_cache', 'cv_cache', 'cross16', 'seq', 'seq_mask', 'pos', 'noise', 'plan',
-                                           'stats', 'bar')]
+                                           'stats', 'bar', 'tstats')]
 
 
 class LMSampling(C.Structure):
@@ -64,6 +64,8 @@ def lib():
     L.acb_convtr1d.argtypes = [vp, vp, vp, vp, vp] + [ci] * 10 + [vp]
     L.acb_conv1d_t6.argtypes = [vp, vp, vp, vp, vp] + [ci] * 12 + [vp]
     L.acb_conv1d_t6_tile.argtypes = [ci]
+    L.acb_resblock_supported.argtypes = [ci, ci, ci]
+    L.acb_resblock.argtypes = [vp] * 6 + [ci] * 8 + [vp]
     L.acb_lstm_recurrent.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
     L.acb_lstm_state_bytes.argtypes = [ci, ci]
     L.acb_lstm_state_bytes.restype = i64
@@ -88,7 +90,8 @@ def lib():
                  'acb_rvq_decode', 'acb_lm_create', 'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps',
                  'acb_lm_step_logits', 'acb_lm_launches_per_step', 'acb_lm_rows_pad', 'acb_sample',
                  'acb_device_sm_count', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_debug_chain_latency',
-                 'acb_conv1d_t6', 'acb_conv1d_t6_tile', 'acb_debug_grid_barrier', 'acb_lm_pack_weight', 'acb_lm_debug_step_plan', 'acb_lm_prefill'):
+                 'acb_conv1d_t6', 'acb_conv1d_t6_tile', 'acb_debug_grid_barrier', 'acb_lm_pack_weight', 'acb_lm_debug_step_plan', 'acb_lm_prefill',
+                 'acb_resblock', 'acb_resblock_supported'):
         getattr(L, name).restype = ci
     _lib = L
     return L
@@ -99,7 +102,8 @@ EXPORTS = ['acb_version', 'acb_last_error', 'acb_device_sm_count', 'acb_weight_n
            'acb_lstm_recurrent', 'acb_lstm_state_bytes', 'acb_rvq_encode', 'acb_rvq_decode', 'acb_lm_create',
            'acb_lm_destroy', 'acb_lm_begin', 'acb_lm_steps', 'acb_lm_step_logits', 'acb_lm_rows_pad',
            'acb_lm_launches_per_step', 'acb_lm_debug_gemms', 'acb_lm_uses_pdl', 'acb_sample', 'acb_debug_chain_latency', 'acb_conv1d_t6', 'acb_conv1d_t6_tile',
-           'acb_debug_grid_barrier', 'acb_lm_pack_weight', 'acb_lm_debug_step_plan', 'acb_lm_prefill']
+           'acb_debug_grid_barrier', 'acb_lm_pack_weight', 'acb_lm_debug_step_plan', 'acb_lm_prefill', 'acb_resblock',
+           'acb_resblock_supported']
 
 
 def check(rc: int, what: str = ''):

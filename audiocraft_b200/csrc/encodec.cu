@@ -302,6 +302,327 @@ static int launch_conv1d_tc(const ConvParams& p, int batch, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// SEANetResnetBlock with the identity skip (audiocraft/modules/seanet.py:44-69, true_skip=True) as ONE kernel:
+//     y = x + W2 . elu(b1 + W1 * elu(x)) + b2          W1: k=3 conv C -> C/2,  W2: 1x1 conv C/2 -> C
+// As two layer kernels the block moves x, the hidden tensor (twice) and y through HBM (4 C-equivalents + 1.5 C of hidden traffic)
+// and is bandwidth / latency bound at 64-128 channels (7-8 ms each for 32 x 10 s at 64 channels).  Here a CTA owns 128 time steps
+// of one item: the ELU'd input slab [C][128 + 2 dil] is staged once, GEMM 1 (M = C/2 hidden channels, N = 128 steps, K = 3C; W1
+// streamed in chunks of 16 input channels x 3 taps) leaves the hidden tile in registers, bias + ELU moves it to shared memory (over
+// the slab), GEMM 2 (M = C in chunks of 64 output channels, K = C/2) reads it from there and the epilogue adds bias and the skip.
+// HBM traffic: x once (+ a second L2-hot read for the skip), y once.  Arithmetic: 3xTF32 on mma.sync.m16n8k8 (hi*lo + lo*hi + hi*hi).
+// FLUSH (encoder: RVQ indices must not move): tensor-core accumulation runs over 8 input channels x 3 taps (resp. 16 hidden
+// channels) only and is then added to fp32 registers, as in conv1d_t6 -- the tensor core's own accumulate rounding is what costs
+// index parity on long reductions, not the operand split.
+// Reduction rows of GEMM 1 are ordered (tap, channel): the 8 rows of one k-step are 8 channels at one tap, so with the slab pitch
+// = 8 mod 32 the B-fragment reads are bank-conflict free.
+// ------------------------------------------------------------------------------------------------
+constexpr int RB_TB = 128, RB_XSP = 136, RB_CH = 16;
+struct ResblockParams {
+    const float* x; const float* w1; const float* b1; const float* w2; const float* b2; float* y;
+    int T, dil, pad_left, reflect;
+};
+
+__device__ __forceinline__ void rb_split(float v, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(v);
+    lo = to_tf32(v - __uint_as_float(hi));
+}
+
+template <int HD, bool FLUSH>
+__global__ void __launch_bounds__(HD >= 128 ? 512 : 256, HD >= 128 ? 1 : 2) resblock_kernel(ResblockParams p) {
+    // 256 threads (8 warps) up to 128 channels, 512 (16 warps) at 256 channels: GEMM 1 tiles the hidden channels over WM1 warp rows
+    // of MT1 m16 tiles and 4 warp columns of 32 steps; GEMM 2 (64 output channels per pass) uses 2 warp rows x WN2 warp columns.
+    constexpr int NTHR = HD >= 128 ? 512 : 256, NWARP = NTHR / 32, WM1 = NWARP / 4, MT1 = HD / (16 * WM1), WN2 = NWARP / 2, NT2 = 16 / WN2;
+    constexpr int C = 2 * HD, WP1 = HD + 8, WP2 = 64 + 8;
+    constexpr bool EARLY_SKIP = !FLUSH || HD == 32;
+    constexpr bool PF_W2 = !(FLUSH && HD == 64);      // next W2 chunk prefetched into registers during the MMAs (registers permitting)   // skip-connection loads before the MMAs of a pass (registers permitting) or after
+    constexpr int WHALF = (3 * RB_CH * WP1) > (HD * WP2) ? (3 * RB_CH * WP1) : (HD * WP2);
+    constexpr int NSL = C * RB_XSP / NTHR, SLB = 17;   // slab elements per thread (34 / 68 / 136), requested 17 at a time
+    constexpr int NW1 = 3 * RB_CH * HD / NTHR;         // W1 chunk elements per thread (6 / 12 / 24)
+    constexpr int NW2 = HD * 64 / NTHR;                // W2 chunk elements per thread (8 / 16 / 32)
+    static_assert(NSL % SLB == 0 && C * RB_XSP % NTHR == 0, "slab staging");
+    extern __shared__ float rsm[];
+    float* xs = rsm;                 // [C][RB_XSP] elu(x); after GEMM 1: [HD][RB_XSP] elu(hidden)
+    float* wh = xs + C * RB_XSP;     // weight chunk, tf32 hi
+    float* wl = wh + WHALF;          // weight chunk, tf32 lo
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+    const int wm = warp % WM1, wn = warp / WM1;     // GEMM 1
+    const int wm2 = warp & 1, wn2 = warp >> 1;      // GEMM 2
+    const int t0 = blockIdx.x * RB_TB, b = blockIdx.y;
+    const float* __restrict__ xb = p.x + (size_t)b * C * p.T;
+    const float* __restrict__ w1g = p.w1;
+    const float* __restrict__ w2g = p.w2;
+    const int span = RB_TB + 2 * p.dil;
+
+    // Every global read below is requested in batches BEFORE anything of the batch is consumed or stored: a load -> store -> load
+    // chain through shared memory (the compiler has to assume aliasing) costs one L2 round trip per element.
+    float w1r[NW1];
+    auto load_w1 = [&](int ci0) {
+#pragma unroll
+        for (int i = 0; i < NW1; ++i) {
+            const int idx = tid + NTHR * i, r = idx / HD, m = idx - r * HD, tap = r / RB_CH, cl = r - tap * RB_CH;
+            w1r[i] = __ldg(w1g + ((size_t)tap * C + ci0 + cl) * HD + m);
+        }
+    };
+    load_w1(0);
+#pragma unroll 1
+    for (int i0 = 0; i0 < NSL; i0 += SLB) {
+        float v[SLB];
+#pragma unroll
+        for (int i = 0; i < SLB; ++i) {
+            const int idx = tid + NTHR * (i0 + i), ch = idx / RB_XSP, j = idx - ch * RB_XSP;
+            int gt = t0 - p.pad_left + j;
+            if (p.reflect) {
+                if (gt < 0) gt = -gt;
+                if (gt >= p.T) gt = 2 * (p.T - 1) - gt;
+            }
+            v[i] = (j < span && gt >= 0 && gt < p.T) ? __ldg(xb + (size_t)ch * p.T + gt) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < SLB; ++i) xs[tid + NTHR * (i0 + i)] = acb_elu(v[i]);
+    }
+
+    float acc1[MT1][4][4];
+#pragma unroll
+    for (int i = 0; i < MT1; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc1[i][j][0] = acc1[i][j][1] = acc1[i][j][2] = acc1[i][j][3] = 0.f;
+
+#pragma unroll 1
+    for (int ci0 = 0; ci0 < C; ci0 += RB_CH) {
+        __syncthreads();   // slab complete (first pass) / previous weight chunk consumed
+#pragma unroll
+        for (int i = 0; i < NW1; ++i) {
+            const int idx = tid + NTHR * i, r = idx / HD, m = idx - r * HD;
+            uint32_t hi, lo;
+            rb_split(w1r[i], hi, lo);
+            wh[r * WP1 + m] = __uint_as_float(hi);
+            wl[r * WP1 + m] = __uint_as_float(lo);
+        }
+        __syncthreads();
+        if (ci0 + RB_CH < C) load_w1(ci0 + RB_CH);   // next chunk's weights fly during this chunk's MMAs
+#pragma unroll
+        for (int c8 = 0; c8 < RB_CH / 8; ++c8) {
+            float accc[MT1][4][4];
+            if (FLUSH) {
+#pragma unroll
+                for (int i = 0; i < MT1; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) accc[i][j][0] = accc[i][j][1] = accc[i][j][2] = accc[i][j][3] = 0.f;
+            }
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap) {
+                const int kr = tap * RB_CH + c8 * 8;
+                uint32_t ah[MT1][4], al[MT1][4];
+#pragma unroll
+                for (int mt = 0; mt < MT1; ++mt) {
+                    const int m = wm * (16 * MT1) + mt * 16 + g;
+                    ah[mt][0] = __float_as_uint(wh[(kr + c) * WP1 + m]);
+                    ah[mt][1] = __float_as_uint(wh[(kr + c) * WP1 + m + 8]);
+                    ah[mt][2] = __float_as_uint(wh[(kr + c + 4) * WP1 + m]);
+                    ah[mt][3] = __float_as_uint(wh[(kr + c + 4) * WP1 + m + 8]);
+                    al[mt][0] = __float_as_uint(wl[(kr + c) * WP1 + m]);
+                    al[mt][1] = __float_as_uint(wl[(kr + c) * WP1 + m + 8]);
+                    al[mt][2] = __float_as_uint(wl[(kr + c + 4) * WP1 + m]);
+                    al[mt][3] = __float_as_uint(wl[(kr + c + 4) * WP1 + m + 8]);
+                }
+                const float* x0p = xs + (ci0 + c8 * 8 + c) * RB_XSP + tap * p.dil + wn * 32 + g;
+                const float* x1p = x0p + 4 * RB_XSP;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    uint32_t bh0, bl0, bh1, bl1;
+                    rb_split(x0p[nt * 8], bh0, bl0);
+                    rb_split(x1p[nt * 8], bh1, bl1);
+#pragma unroll
+                    for (int mt = 0; mt < MT1; ++mt) {
+                        float (&d)[4] = FLUSH ? accc[mt][nt] : acc1[mt][nt];
+                        mma_tf32(d, al[mt], bh0, bh1);
+                        mma_tf32(d, ah[mt], bl0, bl1);
+                        mma_tf32(d, ah[mt], bh0, bh1);
+                    }
+                }
+            }
+            if (FLUSH) {
+#pragma unroll
+                for (int i = 0; i < MT1; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc1[i][j][0] += accc[i][j][0]; acc1[i][j][1] += accc[i][j][1];
+                        acc1[i][j][2] += accc[i][j][2]; acc1[i][j][3] += accc[i][j][3];
+                    }
+            }
+        }
+    }
+    float w2r[NW2];
+    auto load_w2 = [&](int co0) {
+#pragma unroll
+        for (int i = 0; i < NW2; ++i) {
+            const int idx = tid + NTHR * i, r = idx >> 6, m = idx & 63;
+            w2r[i] = __ldg(w2g + (size_t)r * C + co0 + m);
+        }
+    };
+    if (PF_W2) load_w2(0);
+    __syncthreads();   // every warp is done with the slab and the last W1 chunk
+    // hidden tile -> shared memory (bias + ELU), over the slab
+#pragma unroll
+    for (int mt = 0; mt < MT1; ++mt)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int m = wm * (16 * MT1) + mt * 16 + g + 8 * hrow;
+            const float bv = __ldg(p.b1 + m);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int t = wn * 32 + nt * 8 + 2 * c;
+                *reinterpret_cast<float2*>(xs + m * RB_XSP + t) =
+                    make_float2(acb_elu(acc1[mt][nt][2 * hrow] + bv), acb_elu(acc1[mt][nt][2 * hrow + 1] + bv));
+            }
+        }
+
+    const bool pair_ok = (p.T & 1) == 0;   // row bases even -> the (t, t+1) pairs of the epilogue are 8-byte aligned
+#pragma unroll 1
+    for (int co0 = 0; co0 < C; co0 += 64) {
+        if (co0) __syncthreads();   // previous W2 chunk consumed
+        if (!PF_W2) load_w2(co0);
+#pragma unroll
+        for (int i = 0; i < NW2; ++i) {
+            const int idx = tid + NTHR * i, r = idx >> 6, m = idx & 63;
+            uint32_t hi, lo;
+            rb_split(w2r[i], hi, lo);
+            wh[r * WP2 + m] = __uint_as_float(hi);
+            wl[r * WP2 + m] = __uint_as_float(lo);
+        }
+        __syncthreads();   // W2 chunk (and, first pass, the hidden tile) visible
+        if (PF_W2 && co0 + 64 < C) load_w2(co0 + 64);
+        // the skip connection under this warp's output tile
+        float2 xsk[2][2][NT2];
+        auto load_skip = [&]() {
+    #pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+    #pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int co = co0 + wm2 * 32 + mt * 16 + g + 8 * hrow;
+                    const float* __restrict__ xr = xb + (size_t)co * p.T;
+    #pragma unroll
+                    for (int nt = 0; nt < NT2; ++nt) {
+                        const int t = t0 + wn2 * (8 * NT2) + nt * 8 + 2 * c;
+                        if (pair_ok && t + 1 < p.T) xsk[mt][hrow][nt] = __ldg(reinterpret_cast<const float2*>(xr + t));
+                        else xsk[mt][hrow][nt] = make_float2(t < p.T ? __ldg(xr + t) : 0.f, t + 1 < p.T ? __ldg(xr + t + 1) : 0.f);
+                    }
+                }
+        };
+        if (EARLY_SKIP) load_skip();
+        float acc2[2][NT2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < NT2; ++j) acc2[i][j][0] = acc2[i][j][1] = acc2[i][j][2] = acc2[i][j][3] = 0.f;
+#pragma unroll 1
+        for (int kk = 0; kk < HD; kk += 16) {
+            float accc[2][NT2][4];
+            if (FLUSH) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT2; ++j) accc[i][j][0] = accc[i][j][1] = accc[i][j][2] = accc[i][j][3] = 0.f;
+            }
+#pragma unroll
+            for (int k8 = 0; k8 < 16; k8 += 8) {
+                const int kr = kk + k8;
+                uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int m = wm2 * 32 + mt * 16 + g;
+                    ah[mt][0] = __float_as_uint(wh[(kr + c) * WP2 + m]);
+                    ah[mt][1] = __float_as_uint(wh[(kr + c) * WP2 + m + 8]);
+                    ah[mt][2] = __float_as_uint(wh[(kr + c + 4) * WP2 + m]);
+                    ah[mt][3] = __float_as_uint(wh[(kr + c + 4) * WP2 + m + 8]);
+                    al[mt][0] = __float_as_uint(wl[(kr + c) * WP2 + m]);
+                    al[mt][1] = __float_as_uint(wl[(kr + c) * WP2 + m + 8]);
+                    al[mt][2] = __float_as_uint(wl[(kr + c + 4) * WP2 + m]);
+                    al[mt][3] = __float_as_uint(wl[(kr + c + 4) * WP2 + m + 8]);
+                }
+                const float* h0p = xs + (kr + c) * RB_XSP + wn2 * (8 * NT2) + g;
+                const float* h1p = h0p + 4 * RB_XSP;
+#pragma unroll
+                for (int nt = 0; nt < NT2; ++nt) {
+                    uint32_t bh0, bl0, bh1, bl1;
+                    rb_split(h0p[nt * 8], bh0, bl0);
+                    rb_split(h1p[nt * 8], bh1, bl1);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        float (&d)[4] = FLUSH ? accc[mt][nt] : acc2[mt][nt];
+                        mma_tf32(d, al[mt], bh0, bh1);
+                        mma_tf32(d, ah[mt], bl0, bl1);
+                        mma_tf32(d, ah[mt], bh0, bh1);
+                    }
+                }
+            }
+            if (FLUSH) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT2; ++j) {
+                        acc2[i][j][0] += accc[i][j][0]; acc2[i][j][1] += accc[i][j][1];
+                        acc2[i][j][2] += accc[i][j][2]; acc2[i][j][3] += accc[i][j][3];
+                    }
+            }
+        }
+        if (!EARLY_SKIP) load_skip();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int co = co0 + wm2 * 32 + mt * 16 + g + 8 * hrow;
+                const float bv = __ldg(p.b2 + co);
+                float* yr = p.y + ((size_t)b * C + co) * p.T;
+#pragma unroll
+                for (int nt = 0; nt < NT2; ++nt) {
+                    const int t = t0 + wn2 * (8 * NT2) + nt * 8 + 2 * c;
+                    const float v0 = acc2[mt][nt][2 * hrow] + bv + xsk[mt][hrow][nt].x;
+                    const float v1 = acc2[mt][nt][2 * hrow + 1] + bv + xsk[mt][hrow][nt].y;
+                    if (pair_ok && t + 1 < p.T) {
+                        *reinterpret_cast<float2*>(yr + t) = make_float2(v0, v1);
+                    } else {
+                        if (t < p.T) yr[t] = v0;
+                        if (t + 1 < p.T) yr[t + 1] = v1;
+                    }
+                }
+            }
+    }
+}
+
+template <int HD, bool FLUSH>
+static int launch_resblock_one(const ResblockParams& p, int batch, cudaStream_t s) {
+    constexpr int C = 2 * HD, WP1 = HD + 8, WP2 = 72;
+    constexpr int WHALF = (3 * RB_CH * WP1) > (HD * WP2) ? (3 * RB_CH * WP1) : (HD * WP2);
+    const size_t smem = ((size_t)C * RB_XSP + 2 * (size_t)WHALF) * sizeof(float);
+    ACB_CHECK_CUDA(cudaFuncSetAttribute(resblock_kernel<HD, FLUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(acb_ceil_div(p.T, RB_TB), batch);
+    resblock_kernel<HD, FLUSH><<<grid, HD >= 128 ? 512 : 256, smem, s>>>(p);
+    ACB_LAUNCH_CHECK();
+    return ACB_OK;
+}
+
+extern "C" int acb_resblock_supported(int channels, int kernel, int dilation) {
+    return (channels == 64 || channels == 128 || channels == 256) && kernel == 3 && dilation >= 1 && 2 * dilation <= RB_XSP - RB_TB;
+}
+
+extern "C" int acb_resblock(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int batch,
+                            int channels, int t_len, int kernel, int dilation, int pad_left, int reflect, int exact, void* stream) {
+    ACB_REQUIRE(x && w1 && b1 && w2 && b2 && y && x != y, "acb_resblock: null or aliased pointer");
+    ACB_REQUIRE(acb_resblock_supported(channels, kernel, dilation), "acb_resblock: C=%d k=%d dilation=%d is not built", channels, kernel, dilation);
+    ACB_REQUIRE(batch > 0 && batch <= 65535 && t_len > 0 && pad_left >= 0 && pad_left <= 2 * dilation, "acb_resblock: bad shape");
+    ACB_REQUIRE(!reflect || t_len > 2 * dilation, "acb_resblock: reflect padding needs t_len > %d", 2 * dilation);
+    ResblockParams p{x, w1, b1, w2, b2, y, t_len, dilation, pad_left, reflect};
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (channels) {
+        case 64: return exact ? launch_resblock_one<32, true>(p, batch, s) : launch_resblock_one<32, false>(p, batch, s);
+        case 128: return exact ? launch_resblock_one<64, true>(p, batch, s) : launch_resblock_one<64, false>(p, batch, s);
+        default: return exact ? launch_resblock_one<128, true>(p, batch, s) : launch_resblock_one<128, false>(p, batch, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // conv1d on the 5th-generation tensor cores: tcgen05.mma.kind::tf32 with the accumulator in TMEM, 3xTF32 split.
 //   D[128 time steps (TMEM lanes)][N output channels (TMEM columns)] += A[128][8] . B[N][8]^T   per instruction
 //   A = im2col rows of the staged input slab, B = weight rows, both K-major in the canonical 128-byte-swizzled layout

@@ -156,6 +156,8 @@ class EncodecModel(CompressionModel):
         # the LSTM input projections (one 1x1 conv per layer) always run on the tensor cores: measured 3.9e-6 vs 3.6e-6 latent
         # error for the otherwise-fp32 encoder (the tensor-core error of the conv stack comes from its long reductions)
         self._lstm_prec = _lib.CONV_TF32X3
+        import os as _os
+        self._fuse_blocks = _os.environ.get('ACB_ENCODEC_FUSED_BLOCKS', '1') != '0'   # acb_resblock for the residual blocks it takes
         self._lib = _lib.lib()
         self.cfg = dict(cfg)
         self._channels = cfg['channels']
@@ -283,10 +285,49 @@ class EncodecModel(CompressionModel):
             inp = y
         return inp
 
+    def _fused_block(self, layers, i, prec, T):
+        """layers[i], layers[i+1] = the two convolutions of a SEANetResnetBlock with the identity skip that `acb_resblock` takes
+        (64 / 128 / 256 channels, kernel sizes [3, 1]); every tensor-core precision uses it, 'fp32' (all-FMA) does not."""
+        if prec == _lib.CONV_FP32 or not self._fuse_blocks or i + 1 >= len(layers) or T <= 2 * layers[i].get('dilation', 1):
+            return False
+        a, b = layers[i], layers[i + 1]
+        return (a['kind'] == 'conv' and b['kind'] == 'conv' and a['res'] == 'in' and b['res'] == 'out' and a['stride'] == 1
+                and b['k'] == 1 and b['stride'] == 1 and a['elu'] and b['elu'] and b['cout'] == 2 * a['cout']
+                and bool(self._lib.acb_resblock_supported(b['cout'], a['k'], a['dilation'])))
+
+    def _resblock(self, x, a, b, prec):
+        B, C, T = x.shape
+        if 'w1p' not in a:   # [C*k][C/2] (row = ci*k + tap) -> [k][C][C/2]
+            a['w1p'] = a['w'].view(C, a['k'], a['cout']).permute(1, 0, 2).contiguous()
+        left, _, t_out = conv_geometry(T, a['k'], 1, a['dilation'], self.causal, bool(self.reflect))
+        assert t_out == T
+        y = torch.empty_like(x)
+        exact = int(prec in (_lib.CONV_T6_FLUSH, _lib.CONV_T6_AUTO))
+        _lib.check(self._lib.acb_resblock(_lib.ptr(x), _lib.ptr(a['w1p']), _lib.ptr(a['b']), _lib.ptr(b['w']), _lib.ptr(b['b']),
+                                          _lib.ptr(y), B, C, T, a['k'], a['dilation'], left, self.reflect, exact, _lib.stream()),
+                   'resblock')
+        self.launches += 1
+        return y
+
     def _run(self, x, layers, prec=0):
         skip, have_shortcut = None, False
         prof = getattr(self, '_profile', None)   # optional per-layer CUDA-event timing (profiles/perf_encodec.py)
-        for L in layers:
+        skip_next = False
+        for i, L in enumerate(layers):
+            if skip_next:                           # second convolution of a block the fused kernel already ran
+                skip_next = False
+                continue
+            if not have_shortcut and self._fused_block(layers, i, prec, x.shape[-1]):
+                if prof is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    shape_in = tuple(x.shape)
+                x = self._resblock(x, L, layers[i + 1], prec)
+                skip_next = True
+                if prof is not None:
+                    e1.record()
+                    prof.append((dict(L, prefix=L['prefix'] + ' [+1x1, fused block]'), shape_in, tuple(x.shape), e0, e1))
+                continue
             if prof is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

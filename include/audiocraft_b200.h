@@ -75,7 +75,8 @@ int acb_convtr1d(const float* x, const float* w_packed, const float* w_gemm, con
                  int batch, int c_in, int c_out, int t_in, int t_out, int kernel, int stride, int trim_left,
                  int elu_in, int precision, void* stream);
 
-/* EXPERIMENTAL (round-2 candidate, not validated on hardware yet, not used by EncodecModel): the same convolution as
+/* The encoder's default for k > 1, >= 128 output channels (validated on B200 in round 2: latents within 3e-6 of fp32, RVQ
+ * indices exact on the 10 s goldens): the same convolution as
  * acb_conv1d (StreamableConv1d.forward, modules/conv.py:185-201, + fused ELU / residual) as an implicit GEMM on tcgen05
  * without an im2col tile, the TMEM accumulator flushed into fp32 registers once per 8 input channels (csrc/encodec.cu,
  * conv1d_t6_kernel).  c_in % 8 == 0 and c_out % 64 == 0.  w6 = weights split into two tf32 terms and laid out as
@@ -85,6 +86,15 @@ int acb_conv1d_t6(const float* x, const float* w6, const float* bias, const floa
                   int c_in, int c_out, int t_in, int t_virtual, int t_out, int kernel, int stride, int dilation,
                   int pad_left, int reflect, int elu_in, void* stream);
 int acb_conv1d_t6_tile(int c_out);   /* output-channel tile (128, 64, or 0 = shape not supported) */
+/* SEANetResnetBlock.forward with the identity skip (audiocraft/modules/seanet.py:44-69, true_skip=True; one residual layer of
+ * kernel sizes [k, 1]) as one kernel:  y = x + conv1x1(elu(conv_k(elu(x)))).  w1 is the first conv's folded weight packed
+ * [k][C][C/2] (tap-major), w2 the second conv's packed [C/2][C]; pad_left / reflect as acb_conv1d (stride 1).  3xTF32 on the
+ * tensor pipe; exact != 0 bounds every tensor-core accumulation run to 24 (resp. 16) reduction rows with fp32 adds in between
+ * (the encoder setting: RVQ indices equal the fp32 reference's).  x and y must not alias. */
+int acb_resblock_supported(int channels, int kernel, int dilation);
+int acb_resblock(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int batch,
+                 int channels, int t_len, int kernel, int dilation, int pad_left, int reflect, int exact, void* stream);
+
 /* w_gemm (optional, needed for precision ACB_CONV_TF32X3): the same weights packed as the GEMM operand
  * [2*Cin][Cout*stride], row r = ci*2 + k (k = 0 multiplies x[ti-1], k = 1 multiplies x[ti]), column n' = co*stride + ph,
  * value w[ci][ph + (1-k)*stride][co]: the transposed conv then runs on the tcgen05 kernel as one GEMM whose accumulator
@@ -182,6 +192,8 @@ typedef struct {
     void* plan;        /* ACB_LM_PLAN_BYTES of scratch (split-KV attention records of the per-phase path) */
     float* stats;      /* [8][rows_pad][2]  LayerNorm (mean, M2) records per d/8 columns (fused step) */
     void* bar;         /* 128 B: grid-barrier counter of the fused step */
+    float* tstats;     /* [rows_pad][d/16][2]  (mean, M2) of every 16 columns of x: written by the residual GEMM epilogues and the
+                          embedding kernel, merged by the GEMMs that apply LayerNorm on load (default step).  NULL: ACB_LM_STEP=v9 path */
 } acb_lm_buffers;
 
 #define ACB_LM_MAX_SPLIT 8

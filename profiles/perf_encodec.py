@@ -12,7 +12,7 @@ from audiocraft_b200.loaders import load_compression_model  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=32)
 ap.add_argument('--seconds', type=float, default=10.0)
-ap.add_argument('--enc', default='fp32')
+ap.add_argument('--enc', default='fp32_tc')
 ap.add_argument('--dec', default='tf32x3')
 a = ap.parse_args()
 from audiocraft_b200 import synth  # noqa: E402

@@ -85,6 +85,37 @@ def test_experimental_conv1d_t6_matches_oracle(cin, cout, k, s, d, causal, L):
         torch.testing.assert_close(y.cpu(), ref, rtol=2e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize('C,d,causal,L,B', [(64, 1, False, 1000, 2), (64, 1, False, 128, 1), (128, 1, False, 333, 3), (256, 1, False, 257, 2),
+                                           (64, 2, False, 517, 2), (128, 1, True, 130, 2), (64, 1, False, 3, 1), (256, 3, True, 1025, 1)])
+def test_resblock_matches_oracle(C, d, causal, L, B):
+    """SEANetResnetBlock with the identity skip as one kernel (acb_resblock; seanet.py:44-69): y = x + conv1x1(elu(conv3(elu(x)))).
+    exact = 1 (the encoder setting, tensor-core runs cut every 24 / 16 reduction rows) to 2e-5, exact = 0 (3xTF32 straight) to 1e-4 --
+    the tolerances of the flushed / un-flushed single-layer kernels."""
+    from audiocraft_b200.encodec import conv_geometry
+    lib, L_ = _lib()
+    assert L_.acb_resblock_supported(C, 3, d) == 1 and L_.acb_resblock_supported(512, 3, 1) == 0
+    g = torch.Generator().manual_seed(C * 100 + d * 10 + L)
+    x = torch.randn(B, C, L, generator=g)
+    w1 = torch.randn(C // 2, C, 3, generator=g) / (3 * C) ** 0.5
+    b1 = torch.randn(C // 2, generator=g) * 0.3
+    w2 = torch.randn(C, C // 2, 1, generator=g) / (C // 2) ** 0.5
+    b2 = torch.randn(C, generator=g) * 0.3
+    hid = EO.sconv1d(EO.elu(x), w1, b1, stride=1, dilation=d, causal=causal)
+    ref = x + EO.sconv1d(EO.elu(hid), w2, b2, stride=1, dilation=1, causal=causal)
+    left, tv, tout = conv_geometry(L, 3, 1, d, causal, True)
+    assert tout == L and tv == L
+    xd, b1d, b2d = _dev(x), _dev(b1), _dev(b2)
+    w1d = _dev(w1.permute(2, 1, 0))                 # [k][C][C/2]
+    w2d = _dev(w2[:, :, 0].t())                     # [C/2][C]
+    for exact, tol in ((1, 2e-5), (0, 1e-4)):
+        y = torch.full((B, C, L), float('nan'), device='cuda')
+        lib.check(L_.acb_resblock(lib.ptr(xd), lib.ptr(w1d), lib.ptr(b1d), lib.ptr(w2d), lib.ptr(b2d), lib.ptr(y), B, C, L, 3, d,
+                                  left, 1, exact, lib.stream()))
+        torch.cuda.synchronize()
+        print(f'resblock C={C} dil={d} L={L} exact={exact}: max err {(y.cpu() - ref).abs().max():.2e}')
+        torch.testing.assert_close(y.cpu(), ref, rtol=tol, atol=tol)
+
+
 @pytest.mark.parametrize('cin,cout,s,causal,ratio,L', [
     (16, 8, 2, False, 1.0, 37), (8, 16, 3, True, 1.0, 20), (32, 16, 4, False, 1.0, 101), (12, 6, 5, False, 1.0, 50),
     (64, 32, 8, False, 1.0, 50), (8, 4, 4, True, 0.5, 33), (8, 4, 8, True, 0.0, 1), (70, 66, 4, False, 1.0, 70),
