@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libaudiocraft_b200.so')
+LIB_PATH = os.environ.get('ACB_LIB') or os.path.join(_HERE, 'libaudiocraft_b200.so')   # ACB_LIB: the instrumented (timeline) build, debugging only
 
 CONV_FP32, CONV_TF32X3, CONV_TF32X3_MMASYNC = 0, 1, 2
 CONV_T6_FLUSH = 3   # host-side selector only: every layer acb_conv1d_t6 supports goes through it, the rest fp32 FMA
@@ -34,7 +34,7 @@ class LMWeights(C.Structure):
 class LMBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('x', 'h16', 'a16', 'f16', 'q32', 'part', 'logits', 'k_cache', 'v_cache',
                                            'ck_cache', 'cv_cache', 'cross16', 'seq', 'seq_mask', 'pos', 'noise', 'plan',
-                                           'stats', 'bar', 'tstats')]
+                                           'stats', 'bar')]
 
 
 class LMSampling(C.Structure):

@@ -20,8 +20,12 @@ FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=s
          '-Xptxas', '-v']
 if os.environ.get('ACB_STEP_NCW'):   # experiment: compute warps per CTA of the fused decode step (csrc/lm_step.cu)
     FLAGS.append('-DACB_STEP_NCW=' + os.environ['ACB_STEP_NCW'])
+OBJ_SUFFIX = '.o'
 if os.environ.get('ACB_BUILD_TIMELINE') == '1':   # instrumented build: in-kernel %globaltimer stamps (see csrc/lm.cu tl_stamp)
-    FLAGS.append('-DACB_TIMELINE')
+    FLAGS.append('-DACB_TIMELINE')               # goes to its own file (never the product library): run with ACB_LIB=<that path>
+    LIB = os.path.join(HERE, 'libaudiocraft_b200_timeline.so')
+    STAMP = LIB + '.stamp'
+    OBJ_SUFFIX = '.tl.o'
 
 
 def _digest() -> str:
@@ -40,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for f in SOURCES:
-        obj = os.path.join(CSRC, f.replace('.cu', '.o'))
+        obj = os.path.join(CSRC, f.replace('.cu', OBJ_SUFFIX))
         objs.append(obj)
         cmd = [NVCC] + FLAGS + ['-c', os.path.join(CSRC, f), '-o', obj]
         procs.append((f, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -56,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f'link failed:\n{r.stdout}')
     with open(STAMP, 'w') as fh:
         fh.write(dig)
-    with open(os.path.join(HERE, 'build.log'), 'w') as fh:
+    with open(os.path.join(HERE, 'build.log' if OBJ_SUFFIX == '.o' else 'build_timeline.log'), 'w') as fh:
         fh.write('\n'.join(logs))
     if verbose:
         print('\n'.join(logs))

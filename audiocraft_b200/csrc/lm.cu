@@ -107,7 +107,7 @@ template <bool PF>
 __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict__ emb, const float* __restrict__ inv_freq,
                                                        const int64_t* __restrict__ seq, const int* __restrict__ P,
                                                        float* __restrict__ x, int d, int n_q, int card, int max_seq,
-                                                       int batch, float pos_scale, int rows_real, float* __restrict__ stats) {
+                                                       int batch, float pos_scale, int rows_real) {
     pdl_trigger();
     pdl_wait();
     const int r = blockIdx.x, b = (PF ? r % rows_real : r) % batch, pos = P[0] + (PF ? r / rows_real : 0);
@@ -125,16 +125,6 @@ __global__ void __launch_bounds__(256) lm_embed_kernel(const __half* __restrict_
         const float phase = (float)pos / inv_freq[j];
         v += pos_scale * (i < half_d ? cosf(phase) : sinf(phase));
         x[(size_t)r * d + i] = v;
-        if (stats) {   // (mean, M2) of every 16 columns, for the GEMMs that apply LayerNorm on load (lm_gemm2_kernel)
-            float s = v;
-            s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 1);
-            const float m16 = s * (1.f / 16.f), dv = v - m16;
-            float qq = dv * dv;
-            qq += __shfl_xor_sync(0xffffffffu, qq, 8); qq += __shfl_xor_sync(0xffffffffu, qq, 4);
-            qq += __shfl_xor_sync(0xffffffffu, qq, 2); qq += __shfl_xor_sync(0xffffffffu, qq, 1);
-            if ((threadIdx.x & 15) == 0) reinterpret_cast<float2*>(stats)[(size_t)r * (d >> 4) + (i >> 4)] = make_float2(m16, qq);
-        }
     }
 }
 
@@ -195,7 +185,7 @@ __global__ void __launch_bounds__(LN_THREADS) lm_ln_kernel(float* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------ skinny GEMM
-enum { EPI_PARTIAL = 0, EPI_QKV = 1, EPI_GELU = 2, EPI_F32 = 3, EPI_CROSSKV = 4, EPI_QKV_PF = 5, EPI_RESID = 6 };   // _PF: prompt prefill, rows are (token, row) pairs
+enum { EPI_PARTIAL = 0, EPI_QKV = 1, EPI_GELU = 2, EPI_F32 = 3, EPI_CROSSKV = 4, EPI_QKV_PF = 5 };   // _PF: prompt prefill, rows are (token, row) pairs
 
 struct GemmParams {
     const __half* W;  // [N][K] fp16, reference layout
@@ -207,9 +197,6 @@ struct GemmParams {
     int text_len, row0;                                                      // CROSSKV
     int rows_real;                                                           // QKV_PF: rows of the generation (GEMM row = tok * rows_real + row)
     unsigned long long* timing;                 // debug timeline
-    // lm_gemm2_kernel: LayerNorm-on-load operand (x32 [rows][K] fp32, its (mean, M2) records per 16 columns, gamma / beta [K]) and
-    // the records EPI_RESID writes for the x it updates (out_f32 = x, ld_out = N = d)
-    const float* x32; const float* stats_in; const float* gamma; const float* beta; float* stats_out;
 };
 
 // CTA = 4 warps, tile = 16 output features x kslice of K.  The CTA's 16 x kslice weight slab is fetched by ONE thread
@@ -337,333 +324,6 @@ __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
             const int which = n / p.d, nn = n % p.d, h = nn >> 6, dd = nn & 63;
             __half* cache = which ? p.vc : p.kc;
             cache[(((size_t)r * p.H + h) * p.cache_len + tc) * 64 + dd] = __float2half_rn(v);
-        }
-    }
-    tl_stamp(p.timing, 3);
-}
-
-
-// ------------------------------------------------------------------------------------------------ skinny GEMM, cluster split-K
-// Second generation of the step GEMM (the default step; ACB_LM_STEP=v9 keeps the kernels above).  Two changes remove the three
-// residual + LayerNorm kernels of a layer from the dependent chain (11 -> 8 kernels per layer):
-//   * split-K lives inside a thread-block CLUSTER (cluster = the K slices of one feature tile, <= 8 CTAs): ranks 1.. push their
-//     reduced 16*FT2 x rows tile into the rank-0 CTA's shared memory (st.shared::cluster) and arrive on its mbarrier (one release
-//     per warp); rank 0 waits on that mbarrier, sums the slots in rank order (bit-reproducible) and runs the epilogue.  No partial
-//     sums in global memory, no consumer-side reduction, and no cluster-wide barrier on the critical path (the only
-//     barrier.cluster -- "every CTA of the cluster is resident, rank 0's mbarrier is initialised" -- sits before griddepcontrol.wait).
-//     (First version: barrier.cluster + ld.shared::cluster by rank 0 -- 1.6-2.6 us from k-loop end to the reduced tile,
-//     profiles/r2_lm_timeline_v10_*.log.)
-//   * EPI_RESID (out-projections, linear2): x += tile, and the (mean, M2) of every 16 new x values of a row goes to
-//     stats[row][feature / 16].  The GEMMs that consume LayerNorm(x) (QKV, cross-attention query, linear1, output heads) merge a
-//     row's d/16 records in a fixed order (Chan et al.), normalise THEIR K slice of the fp32 residual stream while staging it
-//     to shared memory as fp16, and never see a LayerNorm kernel.  gamma / beta slices are fetched before griddepcontrol.wait.
-// Numerically this is the reference's fp32 LayerNorm (autocast keeps layer_norm in fp32, transformer.py:568-590) followed by the
-// fp16 rounding of the linear's input.
-__device__ __forceinline__ void cluster_arrive_() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-// shared-memory address of `local` in the CTA of rank `rank` of this cluster
-__device__ __forceinline__ uint32_t peer_addr(const void* local, uint32_t rank) {
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
-    return ra;
-}
-__device__ __forceinline__ void st_peer_f32(uint32_t addr, float v) {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_peer(uint32_t addr) {   // release at cluster scope: this thread's earlier DSMEM stores are visible to the waiter
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-
-constexpr int G2_LN_KSLICE_MAX = 1024;   // LayerNorm-on-load GEMMs stage <= 2 float4 per thread and row
-
-template <int NT, int EPI, int FT2>
-__global__ void __launch_bounds__(128) lm_gemm2_kernel(GemmParams p) {
-    constexpr bool LNA = EPI != EPI_RESID;           // A operand = LayerNorm(x) built here; RESID reads ready fp16 activations
-    constexpr int U = NT <= 2 ? 4 : (NT <= 4 ? 2 : 1);
-    constexpr int R = 8 * NT, RP = R + 1, FB = 16 * FT2, TPR = 128 / R, NV = FB * R / 128;
-    extern __shared__ __align__(128) unsigned char gsm[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c4 = lane & 3;
-    const int f0 = blockIdx.x * FB;
-    const int k0 = blockIdx.y * p.kslice;
-    const int ks = min(p.kslice, p.K - k0);
-    const int pitch = p.kslice * 2 + 64;
-    const int S = gridDim.y;                         // cluster size = K slices
-    unsigned char* sp = gsm + FB * pitch;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sp);   // [0]: weight slab landed, [1]: peers' tiles landed (rank 0)
-    sp += 16;
-    float* red = reinterpret_cast<float*>(sp); sp += 4 * FB * RP * sizeof(float);
-    float* slots = reinterpret_cast<float*>(sp); sp += (size_t)(S > 1 ? S - 1 : 1) * FB * R * sizeof(float);   // [S-1][FB*R], used in rank 0
-    float* gb = reinterpret_cast<float*>(sp);        // [gamma slice | beta slice]
-    float* mr = gb + 2 * p.kslice;                   // [mean R | rstd R]
-    unsigned char* As = reinterpret_cast<unsigned char*>(mr + 2 * R);   // [R][pitch] fp16, LNA only
-
-    tl_stamp(p.timing, 0);
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        if (S > 1) mbar_init(bar + 1, (uint32_t)(S - 1) * 4u);   // one arrive per warp of every peer
-    }
-    __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(bar, (uint32_t)FB * (uint32_t)ks * 2u);
-#pragma unroll 1
-        for (int r = 0; r < FB; ++r)
-            bulk_g2s(gsm + r * pitch, p.W + (size_t)(f0 + r) * p.K + k0, (uint32_t)ks * 2u, bar);
-    }
-    const int ks4 = ks >> 2;
-    if (LNA) {
-        for (int i = tid; i < ks4; i += 128) {
-            reinterpret_cast<float4*>(gb)[i] = __ldg(reinterpret_cast<const float4*>(p.gamma + k0) + i);
-            reinterpret_cast<float4*>(gb + p.kslice)[i] = __ldg(reinterpret_cast<const float4*>(p.beta + k0) + i);
-        }
-    }
-    if (S > 1) {   // all CTAs of the cluster resident and rank 0's mbarrier initialised before anyone stores into a peer (off the critical path)
-        cluster_arrive_();
-        cluster_wait_();
-    }
-    pdl_trigger();
-    pdl_wait();   // activations, x and the statistics written by the previous kernels are visible from here on
-    tl_stamp(p.timing, 1);
-    int cache_pos = 0;
-    if (EPI == EPI_QKV || EPI == EPI_QKV_PF) cache_pos = p.pos[0];
-
-    float xo[NV];                                    // RESID, rank 0: the residual stream under this tile, requested now
-    if (EPI == EPI_RESID) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int idx = tid + 128 * i, row = idx / FB, feat = idx % FB;
-            xo[i] = (blockIdx.y == 0 && row < p.rows) ? __ldcg(p.out_f32 + (size_t)row * p.ld_out + f0 + feat) : 0.f;
-        }
-    }
-
-    if (LNA) {
-        // Every global load of a row batch (and the statistics records) is requested before anything is consumed: one L2 round
-        // trip per batch.  RB rows x <= 2 float4 per thread.
-        constexpr int RB = R < 16 ? R : 16;
-        // Row statistics first (they gate everything): TPR consecutive lanes share a row and each takes every TPR-th (mean, M2)
-        // record of 16 columns.  Shifted single-pass sums about the row's first record mean p0 (no cancellation when |mean| >> std):
-        //   mean = p0 + S1 / n,   M2 = sum M2_i + 16 (S2 - S1^2 / n),   S1 = sum (m_i - p0), S2 = sum (m_i - p0)^2
-        // summed per lane in record order, then over the lanes with an xor butterfly (commutative adds: every lane of the row ends with
-        // the same bits, and the result does not depend on which CTA computes it).
-        const int srow = tid / TPR, sq = tid % TPR, n_rec = p.K >> 4;
-        const bool srow_live = srow < p.rows;
-        const float2* rec = reinterpret_cast<const float2*>(p.stats_in) + (size_t)srow * n_rec;
-        float s1 = 0.f, s2 = 0.f, sm2 = 0.f;
-        float pivot = 0.f;
-        constexpr int RCB = NT <= 2 ? 16 : 8;
-#pragma unroll 1
-        for (int i0 = sq; i0 < n_rec; i0 += RCB * TPR) {
-            float2 rc[RCB];
-            const float2 r00 = srow_live ? __ldcg(rec) : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int e = 0; e < RCB; ++e)
-                rc[e] = (srow_live && i0 + e * TPR < n_rec) ? __ldcg(rec + i0 + e * TPR) : make_float2(0.f, 0.f);
-            pivot = r00.x;
-#pragma unroll
-            for (int e = 0; e < RCB; ++e) {
-                if (i0 + e * TPR < n_rec) {
-                    const float dm = rc[e].x - pivot;
-                    s1 += dm;
-                    s2 = fmaf(dm, dm, s2);
-                    sm2 += rc[e].y;
-                }
-            }
-        }
-#pragma unroll 1
-        for (int r0 = 0; r0 < R; r0 += RB) {
-            float4 xv[RB][2];
-#pragma unroll
-            for (int rr = 0; rr < RB; ++rr)
-#pragma unroll
-                for (int ci = 0; ci < 2; ++ci) {
-                    const int c = tid + 128 * ci;
-                    xv[rr][ci] = (c < ks4 && r0 + rr < p.rows)
-                                     ? __ldcg(reinterpret_cast<const float4*>(p.x32 + (size_t)(r0 + rr) * p.K + k0) + c)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            if (r0 == 0) {
-#pragma unroll
-                for (int off = TPR >> 1; off; off >>= 1) {
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-                    sm2 += __shfl_xor_sync(0xffffffffu, sm2, off);
-                }
-                if (sq == 0) {
-                    const float inv_n = 1.f / (float)n_rec;
-                    const float m2 = sm2 + 16.f * (s2 - s1 * s1 * inv_n);
-                    mr[srow] = pivot + s1 * inv_n;
-                    mr[R + srow] = srow_live ? 1.f / sqrtf(fmaxf(m2, 0.f) / (float)p.K + 1e-5f) : 0.f;
-                }
-                __syncthreads();   // mr, and the gamma / beta slices staged before the wait
-                tl_stamp(p.timing, 4);
-            }
-#pragma unroll
-            for (int ci = 0; ci < 2; ++ci) {
-                const int c = tid + 128 * ci;
-                if (c < ks4) {
-                    const float4 gm = reinterpret_cast<const float4*>(gb)[c], bt = reinterpret_cast<const float4*>(gb + p.kslice)[c];
-#pragma unroll
-                    for (int rr = 0; rr < RB; ++rr) {
-                        const float mean = mr[r0 + rr], rstd = mr[R + r0 + rr];
-                        const float4 a = xv[rr][ci];
-                        const __half2 lo = __floats2half2_rn((a.x - mean) * rstd * gm.x + bt.x, (a.y - mean) * rstd * gm.y + bt.y);
-                        const __half2 hi = __floats2half2_rn((a.z - mean) * rstd * gm.z + bt.z, (a.w - mean) * rstd * gm.w + bt.w);
-                        uint2 pk;
-                        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-                        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                        *reinterpret_cast<uint2*>(As + (size_t)(r0 + rr) * pitch + c * 8) = pk;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        tl_stamp(p.timing, 5);
-    }
-
-    float c[FT2][NT][4];
-#pragma unroll
-    for (int ft = 0; ft < FT2; ++ft)
-#pragma unroll
-        for (int j = 0; j < NT; ++j) c[ft][j][0] = c[ft][j][1] = c[ft][j][2] = c[ft][j][3] = 0.f;
-
-    const int nkb = ks >> 5;
-    const int kbw = (nkb + 3) >> 2;
-    const int kb0 = min(nkb, warp * kbw), kb1 = min(nkb, kb0 + kbw);
-    const unsigned char* wr0 = gsm + g * pitch + 16 * c4;
-    const unsigned char* wr1 = wr0 + 8 * pitch;
-
-    if (LNA) {
-        mbar_wait(bar, 0);
-        const unsigned char* ar = As + g * pitch + 16 * c4;
-#pragma unroll 2
-        for (int kb = kb0; kb < kb1; ++kb) {
-            uint4 xv[NT];
-#pragma unroll
-            for (int j = 0; j < NT; ++j) xv[j] = *reinterpret_cast<const uint4*>(ar + (8 * j) * pitch + kb * 64);
-#pragma unroll
-            for (int ft = 0; ft < FT2; ++ft) {
-                const uint4 wa = *reinterpret_cast<const uint4*>(wr0 + ft * 16 * pitch + kb * 64);
-                const uint4 wb = *reinterpret_cast<const uint4*>(wr1 + ft * 16 * pitch + kb * 64);
-#pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    mma16816(c[ft][j], wa.x, wb.x, wa.y, wb.y, xv[j].x, xv[j].y);
-                    mma16816(c[ft][j], wa.z, wb.z, wa.w, wb.w, xv[j].z, xv[j].w);
-                }
-            }
-        }
-    } else {
-        const __half* xr = p.X + (size_t)g * p.K + k0 + 8 * c4;
-        bool w_ready = false;
-        for (int kb = kb0; kb < kb1; kb += U) {
-            uint4 xv[U][NT];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int j = 0; j < NT; ++j)
-                    xv[u][j] = (kb + u < kb1) ? *reinterpret_cast<const uint4*>(xr + (size_t)(8 * j) * p.K + (size_t)(kb + u) * 32)
-                                              : make_uint4(0, 0, 0, 0);
-            if (!w_ready) { mbar_wait(bar, 0); w_ready = true; tl_stamp(p.timing, 4); }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (kb + u < kb1) {
-#pragma unroll
-                    for (int ft = 0; ft < FT2; ++ft) {
-                        const uint4 wa = *reinterpret_cast<const uint4*>(wr0 + ft * 16 * pitch + (kb + u) * 64);
-                        const uint4 wb = *reinterpret_cast<const uint4*>(wr1 + ft * 16 * pitch + (kb + u) * 64);
-#pragma unroll
-                        for (int j = 0; j < NT; ++j) {
-                            mma16816(c[ft][j], wa.x, wb.x, wa.y, wb.y, xv[u][j].x, xv[u][j].y);
-                            mma16816(c[ft][j], wa.z, wb.z, wa.w, wb.w, xv[u][j].z, xv[u][j].w);
-                        }
-                    }
-                }
-            }
-        }
-        if (!w_ready) mbar_wait(bar, 0);   // never leave with a bulk copy in flight
-    }
-    tl_stamp(p.timing, 2);
-    // cross-warp (split-K inside the CTA) reduction in a fixed order
-#pragma unroll
-    for (int ft = 0; ft < FT2; ++ft)
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            float* r0 = red + (warp * FB + ft * 16 + g) * RP + 8 * j + 2 * c4;
-            r0[0] = c[ft][j][0];
-            r0[1] = c[ft][j][1];
-            r0[8 * RP] = c[ft][j][2];
-            r0[8 * RP + 1] = c[ft][j][3];
-        }
-    __syncthreads();
-    float v[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int idx = tid + 128 * i, row = idx / FB, feat = idx % FB;
-        float a = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) a += red[(w * FB + feat) * RP + row];
-        v[i] = a;
-    }
-    if (S > 1) {   // cluster-uniform
-        if (blockIdx.y != 0) {   // push this K slice's tile into rank 0, signal, leave
-            const uint32_t dst = peer_addr(slots + (size_t)(blockIdx.y - 1) * FB * R + tid, 0);
-#pragma unroll
-            for (int i = 0; i < NV; ++i) st_peer_f32(dst + 128 * 4 * i, v[i]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive_peer(peer_addr(bar + 1, 0));
-            return;
-        }
-        mbar_wait_cluster(bar + 1, 0);
-        for (int rk = 1; rk < S; ++rk) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) v[i] += slots[(size_t)(rk - 1) * FB * R + tid + 128 * i];
-        }
-    }
-    tl_stamp(p.timing, 6);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int idx = tid + 128 * i, row = idx / FB, feat = idx % FB, n = f0 + feat;
-        const bool live = row < p.rows;
-        if (EPI == EPI_RESID) {
-            const float xn = xo[i] + v[i];
-            if (live) p.out_f32[(size_t)row * p.ld_out + n] = xn;
-            float s = xn;   // 16 consecutive lanes = 16 consecutive features of one row
-            s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 1);
-            const float m16 = s * (1.f / 16.f), dv = xn - m16;
-            float qq = dv * dv;
-            qq += __shfl_xor_sync(0xffffffffu, qq, 8); qq += __shfl_xor_sync(0xffffffffu, qq, 4);
-            qq += __shfl_xor_sync(0xffffffffu, qq, 2); qq += __shfl_xor_sync(0xffffffffu, qq, 1);
-            if (live && (lane & 15) == 0)
-                reinterpret_cast<float2*>(p.stats_out)[(size_t)row * (p.N >> 4) + (n >> 4)] = make_float2(m16, qq);
-        } else if (!live) {
-            continue;
-        } else if (EPI == EPI_F32) {
-            p.out_f32[(size_t)row * p.ld_out + n] = v[i];
-        } else if (EPI == EPI_GELU) {
-            p.out_f16[(size_t)row * p.ld_out + n] = __float2half_rn(gelu_erf(half_round(v[i])));
-        } else if (EPI == EPI_QKV) {
-            const int which = n >= 2 * p.d ? 2 : (n >= p.d ? 1 : 0), nn = n - which * p.d;
-            if (which == 0) {
-                p.q32[(size_t)row * p.d + nn] = v[i];
-            } else {
-                __half* cache = which == 2 ? p.vc : p.kc;
-                cache[(((size_t)row * p.H + (nn >> 6)) * p.cache_len + cache_pos) * 64 + (nn & 63)] = __float2half_rn(v[i]);
-            }
-        } else if (EPI == EPI_QKV_PF) {
-            const int which = n >= 2 * p.d ? 2 : (n >= p.d ? 1 : 0), nn = n - which * p.d;
-            if (which == 0) {
-                p.q32[(size_t)row * p.d + nn] = v[i];
-            } else {
-                const int tk = row / p.rows_real, rr = row - tk * p.rows_real;
-                __half* cache = which == 2 ? p.vc : p.kc;
-                cache[(((size_t)rr * p.H + (nn >> 6)) * p.cache_len + cache_pos + tk) * 64 + (nn & 63)] = __float2half_rn(v[i]);
-            }
         }
     }
     tl_stamp(p.timing, 3);
@@ -1137,7 +797,6 @@ struct acb_lm {
     int launches = 0;
     bool has_cross = false;
     bool pdl = true;          // programmatic dependent launch between the kernels of a step
-    bool v10 = true;          // cluster split-K GEMMs + LayerNorm on load (8 kernels per layer); ACB_LM_STEP=v9: the round-1 11-kernel layer
     bool fused = false;       // ACB_LM_STEP=fused / rotary positions: the whole transformer of a step is ONE persistent kernel (lm_step.cu)
     StepLaunch step{};
     unsigned long long* trace = nullptr;   // ACB_LM_STEP_TRACE=1: per-phase %globaltimer stamps of CTA 0
@@ -1152,32 +811,19 @@ constexpr size_t ACB_PLAN_COUNTER_BYTES = 4096;   // first bytes of buffers.plan
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its
 // predecessor in the stream is still running and synchronises itself with griddepcontrol.wait.
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
-                             int cluster_y, Args... args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr[2];
-    int na = 0;
-    if (pdl) {
-        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    if (cluster_y > 1) {   // thread-block cluster along grid.y (the K slices of one feature tile)
-        attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = (unsigned)cluster_y; attr[na].val.clusterDim.z = 1;
-        ++na;
-    }
-    if (na) { cfg.attrs = attr; cfg.numAttrs = na; }
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
                             Args... args) {
-    return launch_kc(kernel, grid, block, smem, s, pdl, 1, args...);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #define ACB_LAUNCH(...) ACB_CHECK_CUDA(launch_k(__VA_ARGS__))
-#define ACB_LAUNCH_CLUSTER(...) ACB_CHECK_CUDA(launch_kc(__VA_ARGS__))
 
 static int nt_for_rows(int rows) { return rows <= 8 ? 1 : (rows <= 16 ? 2 : (rows <= 32 ? 4 : 8)); }
 
@@ -1257,82 +903,6 @@ static int pick_split(int N, int K, int sms, bool allow_split, int* kslice) {
     return ns;
 }
 
-// ---- lm_gemm2_kernel (cluster split-K) launch plumbing
-static size_t gemm2_smem_bytes(int nt, int kslice, int ft2, bool lna, int nsplit) {
-    const size_t fb = 16 * ft2, r = 8 * nt, pitch = (size_t)kslice * 2 + 64;
-    size_t b = fb * pitch + 16 + 4 * fb * (r + 1) * sizeof(float) + (size_t)(nsplit > 1 ? nsplit - 1 : 1) * fb * r * sizeof(float);
-    if (lna) b += (size_t)2 * kslice * sizeof(float) + 2 * r * sizeof(float) + r * pitch;
-    return b;
-}
-constexpr int GEMM2_MAX_SMEM = 113 * 1024;   // two CTAs per SM: the next kernel's weight slabs land while this one computes
-
-template <int EPI, int FT2>
-static int launch_gemm2_ft(int nt, const GemmParams& p, int nsplit, cudaStream_t s, bool pdl) {
-    dim3 grid(p.N / (16 * FT2), nsplit);
-    const size_t smem = gemm2_smem_bytes(nt, p.kslice, FT2, EPI != EPI_RESID, nsplit);
-    ACB_REQUIRE(smem <= (size_t)GEMM2_MAX_SMEM && p.N % (16 * FT2) == 0 && nsplit >= 1 && nsplit <= 8,
-                "lm_gemm2: tile does not fit (N=%d kslice=%d ft2=%d nsplit=%d)", p.N, p.kslice, FT2, nsplit);
-    ACB_REQUIRE(EPI == EPI_RESID || p.kslice <= G2_LN_KSLICE_MAX, "lm_gemm2: K slice %d too long for the LayerNorm-on-load staging", p.kslice);
-    switch (nt) {
-        case 1: ACB_LAUNCH_CLUSTER((lm_gemm2_kernel<1, EPI, FT2>), grid, dim3(128), smem, s, pdl, nsplit, p); break;
-        case 2: ACB_LAUNCH_CLUSTER((lm_gemm2_kernel<2, EPI, FT2>), grid, dim3(128), smem, s, pdl, nsplit, p); break;
-        case 4: ACB_LAUNCH_CLUSTER((lm_gemm2_kernel<4, EPI, FT2>), grid, dim3(128), smem, s, pdl, nsplit, p); break;
-        default: ACB_LAUNCH_CLUSTER((lm_gemm2_kernel<8, EPI, FT2>), grid, dim3(128), smem, s, pdl, nsplit, p); break;
-    }
-    return ACB_OK;
-}
-template <int EPI>
-static int launch_gemm2(int nt, const GemmParams& p, int nsplit, cudaStream_t s, bool pdl, int ft2) {
-    if (ft2 == 2) {
-        if constexpr (EPI == EPI_QKV_PF) { acb_set_error("lm_gemm2: this epilogue uses 16-feature tiles"); return ACB_ERR_INVALID; }
-        else return launch_gemm2_ft<EPI, 2>(nt, p, nsplit, s, pdl);
-    }
-    return launch_gemm2_ft<EPI, 1>(nt, p, nsplit, s, pdl);
-}
-template <int NT, int EPI, int FT2>
-static cudaError_t gemm2_attr_one() {
-    cudaError_t e = cudaFuncSetAttribute(lm_gemm2_kernel<NT, EPI, FT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_MAX_SMEM);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lm_gemm2_kernel<NT, EPI, FT2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-}
-template <int EPI>
-static cudaError_t gemm2_attr_all() {
-    cudaError_t e;
-    if ((e = gemm2_attr_one<1, EPI, 1>()) != cudaSuccess) return e;
-    if ((e = gemm2_attr_one<2, EPI, 1>()) != cudaSuccess) return e;
-    if ((e = gemm2_attr_one<4, EPI, 1>()) != cudaSuccess) return e;
-    if ((e = gemm2_attr_one<8, EPI, 1>()) != cudaSuccess) return e;
-    if constexpr (EPI != EPI_QKV_PF) {
-        if ((e = gemm2_attr_one<1, EPI, 2>()) != cudaSuccess) return e;
-        if ((e = gemm2_attr_one<2, EPI, 2>()) != cudaSuccess) return e;
-        if ((e = gemm2_attr_one<4, EPI, 2>()) != cudaSuccess) return e;
-        if ((e = gemm2_attr_one<8, EPI, 2>()) != cudaSuccess) return e;
-    }
-    return cudaSuccess;
-}
-// K slices (= cluster size, <= 8) and tile width of a cluster GEMM.  LayerNorm-on-load GEMMs keep slices <= 768 (<= 384 from 32 rows
-// up: the staged activation tile grows with the rows); residual GEMMs follow pick_split.  32-feature tiles when the grid still
-// covers ~90 % of the SMs and two CTAs fit an SM.
-static int pick_split2(int N, int K, int nt, int sms, bool lna, int* kslice, int* ft2) {
-    const int nkb = K / 32, tiles = N / 16;
-    int ns;
-    if (lna) {
-        const int target = nt <= 2 ? 768 : 384;
-        ns = max(acb_ceil_div(K, target), min(4, acb_ceil_div(sms, tiles)));
-    } else {
-        ns = max(acb_ceil_div(K, 1536), acb_ceil_div(2 * sms, tiles));
-    }
-    ns = max(1, min(min(ns, 8), nkb / 2 > 0 ? nkb / 2 : 1));
-    const int kbs = acb_ceil_div(nkb, ns);
-    ns = acb_ceil_div(nkb, kbs);
-    *kslice = kbs * 32;
-    const char* e = getenv("ACB_LM_FT32");
-    const bool wide = !(e && e[0] == '0') && N % 32 == 0 && (N / 32) * ns * 10 >= sms * 9 &&
-                      gemm2_smem_bytes(nt, *kslice, 2, lna, ns) <= (size_t)GEMM2_MAX_SMEM;
-    *ft2 = wide ? 2 : 1;
-    return ns;
-}
-
 static GemmParams base_gemm(const void* W, const void* X, int N, int K, int rows, int kslice) {
     GemmParams p{};
     p.W = (const __half*)W;
@@ -1380,19 +950,13 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
     const size_t ckv_layer = (size_t)c.max_rows * H * c.max_text * 64;
     const float scale = 1.0f / sqrtf(64.f);
     const bool pdl = lm->pdl;
-    // v10 (default): cluster split-K GEMMs, residual update + LayerNorm statistics in the out-projection epilogues, LayerNorm applied
-    // on load by the consuming GEMM -- 8 kernels per layer.  v9 (ACB_LM_STEP=v9): separate residual + LayerNorm kernels -- 11 per layer.
-    const bool v10 = lm->v10;
-    const float* ln_g = nullptr; const float* ln_b = nullptr;   // v10: the LayerNorm the next GEMM applies on load
-    int nl = 0, ks = 0, ft2 = 1;
+    int nl = 0, ks = 0;
 
     if (!gemms_only) {
         if (pf) ACB_LAUNCH(lm_embed_kernel<true>, dim3(rows), dim3(256), 0, s, pdl, (const __half*)lm->w.emb, lm->w.inv_freq,
-                           (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale, rows_real,
-                           v10 ? B.tstats : (float*)nullptr);
+                           (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale, rows_real);
         else ACB_LAUNCH(lm_embed_kernel<false>, dim3(rows), dim3(256), 0, s, pdl, (const __half*)lm->w.emb, lm->w.inv_freq,
-                        (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale, rows,
-                        v10 ? B.tstats : (float*)nullptr);
+                        (const int64_t*)B.seq, (const int*)B.pos, B.x, d, c.n_q, c.card, c.max_seq, lm->batch, c.pos_scale, rows);
         ++nl;
         DBG("lm_embed_kernel", -1);
     }
@@ -1421,7 +985,6 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
     };
     int pending = 0;  // split-K partial sums waiting to be folded into x by the next LN
     auto ln_launch = [&](const float* gamma, const float* beta, int layer) -> int {
-        if (v10) { ln_g = gamma; ln_b = beta; return ACB_OK; }
         if (gemms_only) return ACB_OK;
         ACB_LAUNCH(lm_ln_kernel, dim3(rows), dim3(LN_THREADS), 0, s, pdl, B.x, (const float*)B.part, pending, part_stride, gamma, beta,
                    (__half*)B.h16, d, tl("ln", layer, rows));
@@ -1430,30 +993,6 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         return ACB_OK;
     };
     auto partial_gemm = [&](const __half* W, const void* X, int N, int K, int layer, int id) -> int {
-        const char* what = id == G_O ? "gemm_O" : (id == G_CQ ? "gemm_CQ" : (id == G_CO ? "gemm_CO" : "gemm_FFN2"));
-        if (v10 && id == G_CQ) {   // query projection of LayerNorm(x): reduced inside the cluster, one fp32 copy for the cross attention
-            const int ns = pick_split2(N, K, nt, lm->sms, true, &ks, &ft2);
-            GemmParams p = base_gemm(W, nullptr, N, K, rows, ks);
-            p.x32 = B.x; p.stats_in = B.tstats; p.gamma = ln_g; p.beta = ln_b;
-            p.out_f32 = B.part; p.ld_out = N;
-            p.timing = tl(what, layer, (N / (16 * ft2)) * ns);
-            ACB_TRY(launch_gemm2<EPI_F32>(nt, p, ns, s, pdl, ft2));
-            ++nl;
-            DBG("gemm2_EPI_F32", layer);
-            pending = 1;
-            return ACB_OK;
-        }
-        if (v10) {                 // x += W a, plus the (mean, M2) records the next LayerNorm-on-load GEMM merges
-            const int ns = pick_split2(N, K, nt, lm->sms, false, &ks, &ft2);
-            GemmParams p = base_gemm(W, X, N, K, rows, ks);
-            p.out_f32 = B.x; p.ld_out = N; p.stats_out = B.tstats;
-            p.timing = tl(what, layer, (N / (16 * ft2)) * ns);
-            ACB_TRY(launch_gemm2<EPI_RESID>(nt, p, ns, s, pdl, ft2));
-            ++nl;
-            DBG("gemm2_EPI_RESID", layer);
-            pending = 0;
-            return ACB_OK;
-        }
         const int ns = pick_split(N, K, lm->sms, true, &ks);
         GemmParams p = base_gemm(W, X, N, K, rows, ks);
         p.out_f32 = B.part; p.ld_out = N; p.split_stride = part_stride;
@@ -1469,19 +1008,7 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         const float* ln = lm->w.ln + (size_t)l * 6 * d;
         // --- self attention
         ACB_TRY(ln_launch(ln, ln + d, l));
-        if (v10) {
-            const int ns = pick_split2(3 * d, d, nt, lm->sms, true, &ks, &ft2);
-            if (pf) ft2 = 1;
-            GemmParams p = base_gemm((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, nullptr, 3 * d, d, rows, ks);
-            p.x32 = B.x; p.stats_in = B.tstats; p.gamma = ln_g; p.beta = ln_b;
-            p.q32 = B.q32; p.kc = (__half*)B.k_cache + l * kv_layer; p.vc = (__half*)B.v_cache + l * kv_layer;
-            p.d = d; p.H = H; p.cache_len = c.max_seq; p.pos = B.pos; p.rows_real = rows_real;
-            p.timing = tl("gemm_QKV", l, 3 * d / (16 * ft2) * ns);
-            if (pf) ACB_TRY(launch_gemm2<EPI_QKV_PF>(nt, p, ns, s, pdl, 1));
-            else ACB_TRY(launch_gemm2<EPI_QKV>(nt, p, ns, s, pdl, ft2));
-            ++nl;
-            DBG("gemm2_EPI_QKV", l);
-        } else {
+        {
             pick_split(3 * d, d, lm->sms, false, &ks);
             GemmParams p = base_gemm((const __half*)lm->w.w_qkv + (size_t)l * 3 * d * d, B.h16, 3 * d, d, rows, ks);
             p.q32 = B.q32; p.kc = (__half*)B.k_cache + l * kv_layer; p.vc = (__half*)B.v_cache + l * kv_layer;
@@ -1529,15 +1056,7 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         }
         // --- feed forward
         ACB_TRY(ln_launch(ln + 4 * d, ln + 5 * d, l));
-        if (v10) {
-            const int ns = pick_split2(ffn, d, nt, lm->sms, true, &ks, &ft2);
-            GemmParams p = base_gemm((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, nullptr, ffn, d, rows, ks);
-            p.x32 = B.x; p.stats_in = B.tstats; p.gamma = ln_g; p.beta = ln_b;
-            p.out_f16 = (__half*)B.f16; p.ld_out = ffn;
-            p.timing = tl("gemm_FFN1", l, ffn / (16 * ft2) * ns);
-            ACB_TRY(launch_gemm2<EPI_GELU>(nt, p, ns, s, pdl, ft2)); ++nl;
-            DBG("gemm2_EPI_GELU", l);
-        } else {
+        {
             pick_split(ffn, d, lm->sms, false, &ks);
             GemmParams p = base_gemm((const __half*)lm->w.w_ff1 + (size_t)l * ffn * d, B.h16, ffn, d, rows, ks);
             p.out_f16 = (__half*)B.f16; p.ld_out = ffn;
@@ -1553,15 +1072,7 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
         return ACB_OK;
     }
     ACB_TRY(ln_launch(lm->w.out_norm, lm->w.out_norm + d, -1));
-    if (v10) {
-        const int N = c.n_q * c.card;
-        const int ns = pick_split2(N, d, nt, lm->sms, true, &ks, &ft2);
-        GemmParams p = base_gemm(lm->w.heads, nullptr, N, d, rows, ks);
-        p.x32 = B.x; p.stats_in = B.tstats; p.gamma = ln_g; p.beta = ln_b;
-        p.out_f32 = B.logits; p.ld_out = N;
-        ACB_TRY(launch_gemm2<EPI_F32>(nt, p, ns, s, pdl, ft2)); ++nl;
-        DBG("gemm2_EPI_F32", -1);
-    } else {
+    {
         const int N = c.n_q * c.card;
         pick_split(N, d, lm->sms, false, &ks);
         GemmParams p = base_gemm(lm->w.heads, B.h16, N, d, rows, ks);
@@ -1639,11 +1150,6 @@ extern "C" int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, 
     if (ea == cudaSuccess) ea = gemm_attr_all<EPI_F32>();
     if (ea == cudaSuccess) ea = gemm_attr_all<EPI_CROSSKV>();
     if (ea == cudaSuccess) ea = gemm_attr_all<EPI_QKV_PF>();
-    if (ea == cudaSuccess) ea = gemm2_attr_all<EPI_QKV>();
-    if (ea == cudaSuccess) ea = gemm2_attr_all<EPI_GELU>();
-    if (ea == cudaSuccess) ea = gemm2_attr_all<EPI_F32>();
-    if (ea == cudaSuccess) ea = gemm2_attr_all<EPI_RESID>();
-    if (ea == cudaSuccess) ea = gemm2_attr_all<EPI_QKV_PF>();
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_cross_attn_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1734,8 +1240,6 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
         // (~2.3 us of grid barrier + skew per phase against 0.9 us per PDL kernel boundary).
         lm->fused = lm->w.wp_qkv != nullptr && ((ev && ev[0] == 'f') || c.positional_embedding != 0);
         ACB_REQUIRE(c.positional_embedding == 0 || lm->fused, "acb_lm_begin: rotary positions are built in the fused decode step only");
-        // default per-phase step: cluster GEMMs with LayerNorm on load (v10); ACB_LM_STEP=v9 (or v5) keeps the 11-kernel layer
-        lm->v10 = lm->buf.tstats != nullptr && !(ev && ev[0] == 'v' && (ev[1] == '9' || ev[1] == '5'));
         if (lm->fused) {
             ACB_TRY(lm_step_prepare(c, lm->w, lm->buf, rows, batch, text_len, lm->has_cross, lm->sms, &lm->step));
             if (env_int("ACB_LM_COOP", 1) == 0) lm->step.cooperative = false;

@@ -176,7 +176,6 @@ class LMModel:
         b['part'] = torch.zeros((_lib.ACB_LM_PART_SLOTS, rp, max(3 * d, self.ffn_dim, self.n_q * self.card)), device=dev, dtype=f32)
         b['stats'] = torch.zeros((8, rp, 2), device=dev, dtype=f32)
         b['bar'] = torch.zeros(32, device=dev, dtype=torch.int32)
-        b['tstats'] = torch.zeros((rp, d // 16, 2), device=dev, dtype=f32)
         b['logits'] = torch.zeros((rp, self.n_q * self.card), device=dev, dtype=f32)
         b['k_cache'] = torch.zeros((L, max_rows, H, max_seq, 64), device=dev, dtype=f16)
         b['v_cache'] = torch.zeros((L, max_rows, H, max_seq, 64), device=dev, dtype=f16)
@@ -202,7 +201,7 @@ class LMModel:
                                                               'wp_o', 'wp_cq', 'wp_co', 'wp_ff1', 'wp_ff2', 'wp_heads', 'rope_freq')])
         bufs = _lib.LMBuffers(*[_lib.ptr(b[n]) for n in ('x', 'h16', 'a16', 'f16', 'q32', 'part', 'logits', 'k_cache',
                                                          'v_cache', 'ck_cache', 'cv_cache', 'cross16', 'seq',
-                                                         'seq_mask', 'pos', 'noise', 'plan', 'stats', 'bar', 'tstats')])
+                                                         'seq_mask', 'pos', 'noise', 'plan', 'stats', 'bar')])
         handle = C.c_void_p()
         _lib.check(self._lib.acb_lm_create(C.byref(cfg), C.byref(wts), C.byref(bufs), C.byref(handle)), 'lm_create')
         self._handle = handle

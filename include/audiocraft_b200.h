@@ -192,8 +192,6 @@ typedef struct {
     void* plan;        /* ACB_LM_PLAN_BYTES of scratch (split-KV attention records of the per-phase path) */
     float* stats;      /* [8][rows_pad][2]  LayerNorm (mean, M2) records per d/8 columns (fused step) */
     void* bar;         /* 128 B: grid-barrier counter of the fused step */
-    float* tstats;     /* [rows_pad][d/16][2]  (mean, M2) of every 16 columns of x: written by the residual GEMM epilogues and the
-                          embedding kernel, merged by the GEMMs that apply LayerNorm on load (default step).  NULL: ACB_LM_STEP=v9 path */
 } acb_lm_buffers;
 
 #define ACB_LM_MAX_SPLIT 8

@@ -421,28 +421,6 @@ def test_fused_step_matches_per_phase_kernels(monkeypatch, name, B):
     assert (out_f == out_b).float().mean() > 0.9
 
 
-@pytest.mark.parametrize('name,B', [('lm_mini', 1), ('lm_mini', 3), ('lm_medium_2l', 8), ('lm_medium_2l', 20), ('lm_large_2l', 8)])
-def test_default_step_matches_separate_layernorm_kernels(monkeypatch, name, B):
-    """The default step (cluster split-K GEMMs; residual add + LayerNorm statistics in the out-projection epilogues, LayerNorm applied
-    on load by the consuming GEMM: 8 kernels per layer) against the round-1 layer of 11 kernels with separate residual + LayerNorm
-    kernels (ACB_LM_STEP=v9): same arithmetic up to the fp32 grouping of the split-K sums and of the LayerNorm statistics."""
-    cfg, sd, m = _model(name, 5)
-    T = 6
-    _, _, cross = H.lm_condition(cfg, sd, B, 5, 1)
-    seq = torch.randint(0, cfg['card'], (B, 4, T + 4), generator=torch.Generator().manual_seed(1))
-    monkeypatch.setenv('ACB_LM_STEP', 'v10')
-    new = m.teacher_forced_logits(seq, cross, 3.0).cpu()
-    assert m.launches_per_step == 8 * cfg['num_layers'] + 3      # embed, 8 per layer, heads, sampler
-    out_n = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross).cpu()
-    monkeypatch.setenv('ACB_LM_STEP', 'v9')
-    base = m.teacher_forced_logits(seq, cross, 3.0).cpu()
-    assert m.launches_per_step == 11 * cfg['num_layers'] + 4
-    out_b = m.generate(None, [], num_samples=B, max_gen_len=T, use_sampling=False, cross_attention_src=cross).cpu()
-    print(f'{name} B={B}: max |v10 - v9| = {(new - base).abs().max():.2e} on |logits| <= {base.abs().max():.1f}')
-    torch.testing.assert_close(new, base, rtol=0, atol=4e-2)   # fp16 roundings of the activations flip on fp32 regrouping (measured 2.0e-2)
-    assert (out_n == out_b).float().mean() > 0.9
-
-
 @pytest.mark.parametrize('name,B,T0', [('lm_mini', 2, 9), ('lm_mini', 5, 23), ('lm_medium_2l', 8, 21)])
 def test_prompt_prefill_equals_token_by_token(monkeypatch, name, B, T0):
     """Prompt prefill (acb_lm_prefill = the reference's multi-token first call, lm.py:513-534, transformer.py:240-247): 64 / rows
