@@ -998,6 +998,22 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
             }
         }
         const float* xb = p.x + (size_t)b * p.c_in * p.t_in;
+        // The raw samples of a channel group are requested as one batch into registers and consumed afterwards: the first version
+        // loaded, ELU'd (a branch on the loaded value) and stored vector by vector -- 20 dependent L2 round trips per group, 53 % of
+        // all stall samples on that branch, 82 us per CTA (profiles/r2_ncu_conv1d_t6_*).  The next group's batch is requested
+        // before this group is published, so its round trip overlaps the fence / barrier / wait for the buffer.
+        float raw[T6_MAXV][4];
+        auto fetch = [&](int cg) {
+#pragma unroll
+            for (int i = 0; i < T6_MAXV; ++i) {
+                const int c = (dst[i] >> 30) & 1;
+                const float* xc = xb + (size_t)(cg * 8 + c * 4) * p.t_in;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    raw[i][q] = (dst[i] >= 0 && src[i] >= 0) ? __ldg(xc + (size_t)q * p.t_in + src[i]) : 0.f;
+            }
+        };
+        fetch(0);
         for (int cg = 0; cg < p.n_cg; ++cg) {
             const int st = cg & 1;
             t6_mbar_wait(a_empty + st, ((cg >> 1) & 1) ^ 1);   // first use of each buffer passes at once
@@ -1006,19 +1022,18 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
 #pragma unroll
             for (int i = 0; i < T6_MAXV; ++i) {
                 if (dst[i] < 0) continue;
-                const int c = (dst[i] >> 30) & 1, off = dst[i] & 0x3FFFFFFF;
-                const float* xc = xb + (size_t)(cg * 8 + c * 4) * p.t_in;
-                float v[4], h[4], l[4];
+                const int off = dst[i] & 0x3FFFFFFF;
+                float h[4], l[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    v[q] = src[i] >= 0 ? __ldg(xc + (size_t)q * p.t_in + src[i]) : 0.f;
-                    if (p.elu) v[q] = acb_elu(v[q]);
-                    h[q] = __uint_as_float(to_tf32(v[q]));
-                    l[q] = __uint_as_float(to_tf32(v[q] - h[q]));
+                    const float v = p.elu ? acb_elu(raw[i][q]) : raw[i][q];
+                    h[q] = __uint_as_float(to_tf32(v));
+                    l[q] = __uint_as_float(to_tf32(v - h[q]));
                 }
                 *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
             }
+            if (cg + 1 < p.n_cg) fetch(cg + 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
             asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four producer warps
             if (tid == 0) t6_mbar_arrive(a_full + st);
@@ -1508,8 +1523,154 @@ __global__ void __launch_bounds__(256) lstm_kernel(LstmParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Recurrent LSTM step on the tensor pipe (hidden % 64 == 0, batch <= 32): 3xTF32 mma.sync.m16n8k8, fp32 accumulate.
+//   gates[32 rows = 4 gates x 8 units of this CTA][32 items] = W_hh slice [32][H] . h_{t-1} [H][32]
+// * CTA = 8 units (H / 8 CTAs, co-resident: cooperative launch), 8 warps; warp w multiplies the K range [w H/8, (w+1) H/8) for all
+//   32 rows x 32 items (2 m16 x 4 n8 tiles, 32 accumulator registers); the 8 partial tiles are summed in shared memory in warp order.
+// * W_hh slice resident in shared memory for the whole sequence (row pitch H + 4 floats: conflict-free A fragments), split into tf32
+//   hi / lo terms on the way into the MMA.
+// * h lives in global memory in the B-FRAGMENT order hF[k / 8][k % 8][item % 8][item / 8]: lane (g, c) fetches its four n-tiles of
+//   k-row c (resp. c + 4) with one 16-byte load, a warp instruction reads 4 x 128 contiguous bytes, every byte fetched is used
+//   (128 KB per CTA and step, the minimum for "every CTA needs all of h"), and nothing is staged through shared memory.
+// * thread (unit u = tid / 32, item b = tid % 32) owns one cell: its c_t stays in a register for the whole sequence, it adds the
+//   input half of the gates (requested one step ahead), applies the nonlinearities and writes h_t (fragment order) and y.
+// * one grid barrier per step (release arrive / acquire poll), h double-buffered.
+// The fp32 FMA kernel above measures 18.2 us per step at H = 1024 (two 16-item passes, each: stage 64 KB of h, 2 048 FFMA per thread,
+// transposing reduction); this one reads h once and does the arithmetic on the tensor pipe.
+// ------------------------------------------------------------------------------------------------
+constexpr int LTC_U = 8, LTC_ROWS = 4 * LTC_U, LTC_B = 32, LTC_NW = 8, LTC_PB = 4;   // 8 warps; B fragments of LTC_PB k-steps requested together
+__global__ void __launch_bounds__(LTC_NW * 32, 1) lstm_tc_kernel(LstmParams p) {
+    extern __shared__ float smem[];
+    const int H = p.H, WP = H + 4;
+    float* wsm = smem;                           // [32][WP]
+    float* red = wsm + (size_t)LTC_ROWS * WP;    // [8 warps][32 rows][33]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+    const int unit0 = blockIdx.x * LTC_U;
+    const unsigned ncta = gridDim.x;
+
+    for (int idx = tid; idx < LTC_ROWS * (H / 4); idx += LTC_NW * 32) {
+        const int r = idx / (H / 4), c4 = idx - r * (H / 4), gate = r / LTC_U, u = r - gate * LTC_U;
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.whh + ((size_t)gate * H + unit0 + u) * H) + c4);
+        *reinterpret_cast<float4*>(wsm + (size_t)r * WP + 4 * c4) = w;
+    }
+    __syncthreads();
+
+    const int cu = (tid >> 5) & (LTC_U - 1), cb = tid & 31;   // threads 0..255 own one cell each: unit unit0 + cu, item cb
+    const bool cell_live = tid < LTC_U * 32 && cb < p.B;
+    const int kunit = unit0 + cu;
+    const size_t hf_cell = ((size_t)kunit * 8 + (cb & 7)) * 4 + (cb >> 3);   // hF float index of (k = kunit, item cb)
+    const size_t hf_size = (size_t)H * LTC_B;
+    const size_t gx_cell = ((size_t)cb * 4 * H + kunit) * p.T;               // + gate * H * T + t
+    const size_t y_cell = ((size_t)cb * H + kunit) * p.T;
+    float cstate = 0.f;
+    const int ksteps = H / (8 * LTC_NW);         // k-steps of 8 per warp
+    const int kb0 = warp * ksteps;               // first k-block (of 8) of this warp
+
+    float gxr[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cell_live) {
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) gxr[gt] = __ldg(p.gx + gx_cell + (size_t)gt * H * p.T);
+    }
+    for (int t = 0; t < p.T; ++t) {
+        const float* hprev = p.hbuf + (size_t)(t & 1) * hf_size;
+        float* hnext = p.hbuf + (size_t)((t + 1) & 1) * hf_size;
+        float gi = gxr[0], gf = gxr[1], gg = gxr[2], go = gxr[3];
+        if (cell_live && t + 1 < p.T) {          // next step's input half: in flight during this step's MMAs
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt) gxr[gt] = __ldg(p.gx + gx_cell + (size_t)gt * H * p.T + t + 1);
+        }
+        if (t > 0) {
+            float acc[2][4][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+            const float4* hf4 = reinterpret_cast<const float4*>(hprev);
+            // B fragments are requested LTC_PB k-steps at a time.  Measured per LSTM block (2 layers x 500 steps, H = 1024, 32 items):
+            // 8 warps x 4 k-steps 14.5 ms; 8 warps, all 16 k-steps up front (255 registers) 16.1 ms; 16 warps x all 8 k-steps (128
+            // registers, spills) 17.2 ms; fp32 FMA kernel 18.3 ms (profiles/r2_perf_encodec_v3*.log, v4*.log).
+#pragma unroll 1
+            for (int s0 = 0; s0 < ksteps; s0 += LTC_PB) {
+                float4 b0[LTC_PB], b1[LTC_PB];
+#pragma unroll
+                for (int s = 0; s < LTC_PB; ++s) {
+                    if (s0 + s < ksteps) {       // warp-uniform
+                        const size_t kb = (size_t)(kb0 + s0 + s);
+                        b0[s] = __ldcg(hf4 + (kb * 8 + c) * 8 + g);
+                        b1[s] = __ldcg(hf4 + (kb * 8 + c + 4) * 8 + g);
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < LTC_PB; ++s) {
+                    if (s0 + s >= ksteps) break;
+                    const int k = (kb0 + s0 + s) * 8;
+                    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const float* wr = wsm + (size_t)(mt * 16 + g) * WP + k + c;
+                        rb_split(wr[0], ah[mt][0], al[mt][0]);
+                        rb_split(wr[8 * WP], ah[mt][1], al[mt][1]);
+                        rb_split(wr[4], ah[mt][2], al[mt][2]);
+                        rb_split(wr[8 * WP + 4], ah[mt][3], al[mt][3]);
+                    }
+                    const float bx0[4] = {b0[s].x, b0[s].y, b0[s].z, b0[s].w}, bx1[4] = {b1[s].x, b1[s].y, b1[s].z, b1[s].w};
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        uint32_t bh0, bl0, bh1, bl1;
+                        rb_split(bx0[nt], bh0, bl0);
+                        rb_split(bx1[nt], bh1, bl1);
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            mma_tf32(acc[mt][nt], al[mt], bh0, bh1);
+                            mma_tf32(acc[mt][nt], ah[mt], bl0, bl1);
+                            mma_tf32(acc[mt][nt], ah[mt], bh0, bh1);
+                        }
+                    }
+                }
+            }
+            float* rw = red + (size_t)warp * LTC_ROWS * 33;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    float* r0 = rw + (mt * 16 + g) * 33 + nt * 8 + 2 * c;
+                    r0[0] = acc[mt][nt][0];
+                    r0[1] = acc[mt][nt][1];
+                    r0[8 * 33] = acc[mt][nt][2];
+                    r0[8 * 33 + 1] = acc[mt][nt][3];
+                }
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < LTC_NW; ++w) {   // warp order: fixed summation order
+                const float* rr = red + (size_t)w * LTC_ROWS * 33 + cb;
+                gi += rr[(0 * LTC_U + cu) * 33];
+                gf += rr[(1 * LTC_U + cu) * 33];
+                gg += rr[(2 * LTC_U + cu) * 33];
+                go += rr[(3 * LTC_U + cu) * 33];
+            }
+        }
+        if (cell_live) {
+            cstate = sigmoidf_(gf) * cstate + sigmoidf_(gi) * tanhf(gg);
+            const float h = sigmoidf_(go) * tanhf(cstate);
+            __stcg(hnext + hf_cell, h);
+            p.y[y_cell + t] = p.skip ? h + p.skip[y_cell + t] : h;
+        }
+        // grid barrier: everyone has published h_t (and is done with the partial-sum buffer) before anyone reads it
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(p.bar, 1u);
+            const unsigned target = ncta * (unsigned)(t + 1);
+            while (ld_acquire_u32(p.bar) < target) { }
+        }
+        __syncthreads();
+    }
+}
+
 extern "C" int64_t acb_lstm_state_bytes(int batch, int hidden) {
-    return ((int64_t)2 * batch * hidden + 64) * (int64_t)sizeof(float);
+    const int64_t b = batch > LTC_B ? batch : LTC_B;   // the tensor-core kernel keeps h for 32 item slots
+    return ((int64_t)2 * b * hidden + 64) * (int64_t)sizeof(float);
 }
 
 extern "C" int acb_lstm_recurrent(const float* gates_x, const float* w_hh, const float* skip, float* y,
@@ -1517,6 +1678,27 @@ extern "C" int acb_lstm_recurrent(const float* gates_x, const float* w_hh, const
     ACB_REQUIRE(gates_x && w_hh && y && state_ws, "acb_lstm_recurrent: null pointer");
     ACB_REQUIRE(batch > 0 && hidden > 0 && t_len > 0, "acb_lstm_recurrent: empty shape");
     ACB_REQUIRE(hidden % 4 == 0, "acb_lstm_recurrent: hidden must be a multiple of 4");
+    cudaStream_t s = (cudaStream_t)stream;
+    {   // tensor-core kernel: hidden a multiple of 64, up to 32 items, H / 8 co-resident CTAs; ACB_LSTM_TC=0 keeps the fp32 FMA kernel
+        const char* e = getenv("ACB_LSTM_TC");
+        const size_t smem_tc = ((size_t)LTC_ROWS * (hidden + 4) + (size_t)LTC_NW * LTC_ROWS * 33) * sizeof(float);
+        if (!(e && e[0] == '0') && hidden % (8 * LTC_NW) == 0 && batch <= LTC_B && smem_tc <= 227 * 1024) {
+            const int ncta = hidden / LTC_U;
+            ACB_CHECK_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+            int dev = 0, sms = 0, per_sm = 0;
+            ACB_CHECK_CUDA(cudaGetDevice(&dev));
+            ACB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            ACB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_tc_kernel, LTC_NW * 32, smem_tc));
+            if (per_sm * sms >= ncta) {
+                const size_t hfloats = (size_t)2 * LTC_B * hidden;
+                ACB_CHECK_CUDA(cudaMemsetAsync(state_ws, 0, (hfloats + 64) * sizeof(float), s));
+                LstmParams p{gates_x, w_hh, skip, y, state_ws, (unsigned*)(state_ws + hfloats), batch, hidden, t_len, LTC_U};
+                void* args[] = {&p};
+                ACB_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_kernel, dim3(ncta), dim3(LTC_NW * 32), args, smem_tc, s));
+                return ACB_OK;
+            }
+        }
+    }
     int U = hidden >= 128 ? hidden / 128 : 1;
     ACB_REQUIRE(hidden % U == 0, "acb_lstm_recurrent: hidden %d not divisible by %d units per CTA", hidden, U);
     int ncta = hidden / U;
@@ -1524,7 +1706,6 @@ extern "C" int acb_lstm_recurrent(const float* gates_x, const float* w_hh, const
                   sizeof(float);
     ACB_REQUIRE(smem <= 227 * 1024, "acb_lstm_recurrent: hidden=%d batch=%d needs %zu B smem per CTA", hidden, batch, smem);
     ACB_REQUIRE(U * LSTM_BC <= 256, "acb_lstm_recurrent: too many units per CTA");
-    cudaStream_t s = (cudaStream_t)stream;
     ACB_CHECK_CUDA(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0, per_sm = 0;
     ACB_CHECK_CUDA(cudaGetDevice(&dev));

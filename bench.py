@@ -381,7 +381,7 @@ def run_b200(args):
                         launches_per_generate=S - 1, kernel_ms_per_generate=round(tot_ms, 2), per_kv=pts, whole_generate=whole)
     else:
         gemm_ms = time_dominant(20)
-        tp = os.path.join(ROOT, 'profiles', 'r1_step_kv750_v9_dram_summary.json')   # ncu capture of the per-phase kernels
+        tp = os.path.join(ROOT, 'profiles', 'r2_step_kv751_dram_summary.json')   # ncu launch list + DRAM bytes of the per-phase kernels (round 2)
         if os.path.exists(tp) and args.scale == 'medium' and B == 8:
             tj = json.load(open(tp)).get('lm_gemm_kernel')
             if tj:
