@@ -56,6 +56,32 @@ __device__ __forceinline__ float conv_fetch(const float* __restrict__ xr, int g,
     return elu ? acb_elu(v) : v;
 }
 
+// One warp stages dst[q] = act(x[g0 + q * gstep]) for q in [0, n) (zero beyond, up to n_store): the global loads of 8 lane-strided
+// entries are requested before the first is consumed.  A plain `dst[j] = act(load(j))` loop is a chain of dependent L2 round trips
+// (the activation branches on the loaded value and the compiler cannot move a load above the shared-memory store before it): that
+// pattern was 53 % of conv1d_t6's stall samples and 3x of the fused residual block's run time before it was batched.
+__device__ __forceinline__ void stage_span(float* __restrict__ dst, const float* __restrict__ xr, int g0, int gstep, int n, int n_store,
+                                           int t_in, int t_virt, int reflect, int elu, int lane) {
+    for (int q0 = 0; q0 < n_store; q0 += 256) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int q = q0 + lane + 32 * u;
+            int g = g0 + q * gstep;
+            if (reflect) {
+                if (g < 0) g = -g;
+                if (g >= t_virt) g = 2 * (t_virt - 1) - g;
+            }
+            v[u] = (q < n && g >= 0 && g < t_in) ? __ldg(xr + g) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int q = q0 + lane + 32 * u;
+            if (q < n_store) dst[q] = elu ? acb_elu(v[u]) : v[u];
+        }
+    }
+}
+
 template <int CPT, int TPT>
 __global__ void __launch_bounds__(256) conv1d_kernel(ConvParams p) {
     constexpr int BM = 8 * CPT, BN = 32 * TPT;
@@ -92,13 +118,9 @@ __global__ void __launch_bounds__(256) conv1d_kernel(ConvParams p) {
         for (int cl = warp; cl < nci; cl += 8) {
             const float* xrow = xb + (size_t)(ci0 + cl) * p.t_in;
             float* xdst = xs + cl * XS;
-            if (p.stride == 1) {
-                for (int j = lane; j < p.span; j += 32)
-                    xdst[j] = conv_fetch(xrow, g0 + j, p.t_in, p.t_virt, p.reflect, p.elu);
-            } else {
-                for (int ph = 0; ph < p.stride; ++ph)
-                    for (int q = lane; q * p.stride + ph < p.span; q += 32)
-                        xdst[ph * p.PL + q] = conv_fetch(xrow, g0 + q * p.stride + ph, p.t_in, p.t_virt, p.reflect, p.elu);
+            for (int ph = 0; ph < p.stride; ++ph) {   // stride phase planes (one plane for stride 1)
+                const int nq = (p.span - ph + p.stride - 1) / p.stride;
+                stage_span(xdst + ph * p.PL, xrow, g0 + ph, p.stride, nq, nq, p.t_in, p.t_virt, p.reflect, p.elu, lane);
             }
         }
         __syncthreads();
@@ -221,13 +243,9 @@ __global__ void __launch_bounds__(256) conv1d_tc_kernel(ConvParams p, int xsp, i
         for (int cl = warp; cl < nci; cl += 8) {
             const float* xrow = xb + (size_t)(ci0 + cl) * p.t_in;
             float* xdst = xs + cl * xsp;
-            if (p.stride == 1) {
-                for (int j = lane; j < p.span; j += 32)
-                    xdst[j] = conv_fetch(xrow, g0 + j, p.t_in, p.t_virt, p.reflect, p.elu);
-            } else {
-                for (int ph = 0; ph < p.stride; ++ph)
-                    for (int q = lane; q * p.stride + ph < p.span; q += 32)
-                        xdst[ph * p.PL + q] = conv_fetch(xrow, g0 + q * p.stride + ph, p.t_in, p.t_virt, p.reflect, p.elu);
+            for (int ph = 0; ph < p.stride; ++ph) {
+                const int nq = (p.span - ph + p.stride - 1) / p.stride;
+                stage_span(xdst + ph * p.PL, xrow, g0 + ph, p.stride, nq, nq, p.t_in, p.t_virt, p.reflect, p.elu, lane);
             }
         }
         __syncthreads();
@@ -901,6 +919,7 @@ struct T6Params {
     const float* x; const float* w6; const float* bias; const float* res; float* y;
     int c_in, c_out, t_in, t_virt, t_out, K, S, D, pad_left, reflect, elu;
     int span, PL, n_cg, TB;   // slab length, rows per phase plane, 8-channel groups, taps per weight stage
+    int t_tiles, n_co, n_tiles;   // persistent tile loop: tile -> (time tile, output-channel tile, item)
 };
 
 __device__ __forceinline__ void t6_mbar_init(uint64_t* b, uint32_t count) {
@@ -942,7 +961,9 @@ __host__ __device__ inline T6Smem t6_smem(int N, int S, int PL, int TB) {
     return L;
 }
 
-template <int N>
+// NV = slab vectors per staging thread (4 / 12 / 20): the maps and the prefetched raw samples live in registers, and 10 warps are allocated
+// as 12 (warp allocation granularity 4), which caps the kernel at 168 registers per thread.
+template <int N, int NV>
 __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
     extern __shared__ __align__(128) unsigned char t6sm[];
     const T6Smem L = t6_smem(N, p.S, p.PL, p.TB);
@@ -956,7 +977,11 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t0 = blockIdx.x * T6_M, co0 = blockIdx.y * N, b = blockIdx.z;
+    // PERSISTENT over tiles (one CTA per SM fits: 131 KB of shared memory, 2 N TMEM columns): tile = blockIdx.x, += gridDim.x.  Every
+    // role walks the same tile sequence with running group / stage counters, so the mbarrier pipelines simply continue across tiles:
+    // the staging warps fill the next tile's first slabs and the MMA warp starts on them while the epilogue warps still store the
+    // previous tile.  (One tile per CTA measured 65-82 us per tile of which the 192 MMAs need ~7: prologue, pipeline fill and the
+    // 128-stores-per-thread epilogue ran with nothing else resident on the SM.)
     const int nstage_b = (p.K + p.TB - 1) / p.TB;   // weight stages per channel group
 
     if (warp == 4) {
@@ -980,32 +1005,39 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
         // ================= producers: stage the 8-channel slab of every channel group =================
         // chunk-invariant maps: this thread's (time j, 4-channel chunk c) vectors -> source index / destination
         const int nvec = 2 * p.span;
-        const int g0 = t0 * p.S - p.pad_left;
-        int src[T6_MAXV], dst[T6_MAXV];   // src: input index or -1 (padding) ; dst: byte offset inside one term's slab or -1
+        int src[NV], dst[NV], jj[NV];   // src: input index or -1 (padding); dst: byte offset inside one term's slab or -1; jj: slab step
 #pragma unroll
-        for (int i = 0; i < T6_MAXV; ++i) {
+        for (int i = 0; i < NV; ++i) {   // tile-invariant part of the map (the divisions)
             const int e = tid + 128 * i;
-            src[i] = -1; dst[i] = -1;
+            dst[i] = -1; jj[i] = 0;
             if (e < nvec) {
                 const int c = e / p.span, j = e - c * p.span;
-                int g = g0 + j;
-                if (p.reflect) {
-                    if (g < 0) g = -g;
-                    if (g >= p.t_virt) g = 2 * (p.t_virt - 1) - g;
-                }
                 dst[i] = (((c * p.S + (j % p.S)) * p.PL + j / p.S) * 16) | (c << 30);
-                if (g >= 0 && g < p.t_in) src[i] = g;
+                jj[i] = j;
             }
+        }
+        int G = 0;   // running channel-group counter (slab buffer = G & 1)
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int t0 = (tile % p.t_tiles) * T6_M, b = tile / (p.t_tiles * p.n_co);
+        const int g0 = t0 * p.S - p.pad_left;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            int g = g0 + jj[i];
+            if (p.reflect) {
+                if (g < 0) g = -g;
+                if (g >= p.t_virt) g = 2 * (p.t_virt - 1) - g;
+            }
+            src[i] = (dst[i] >= 0 && g >= 0 && g < p.t_in) ? g : -1;
         }
         const float* xb = p.x + (size_t)b * p.c_in * p.t_in;
         // The raw samples of a channel group are requested as one batch into registers and consumed afterwards: the first version
         // loaded, ELU'd (a branch on the loaded value) and stored vector by vector -- 20 dependent L2 round trips per group, 53 % of
         // all stall samples on that branch, 82 us per CTA (profiles/r2_ncu_conv1d_t6_*).  The next group's batch is requested
         // before this group is published, so its round trip overlaps the fence / barrier / wait for the buffer.
-        float raw[T6_MAXV][4];
+        float raw[NV][4];
         auto fetch = [&](int cg) {
 #pragma unroll
-            for (int i = 0; i < T6_MAXV; ++i) {
+            for (int i = 0; i < NV; ++i) {
                 const int c = (dst[i] >> 30) & 1;
                 const float* xc = xb + (size_t)(cg * 8 + c * 4) * p.t_in;
 #pragma unroll
@@ -1014,13 +1046,13 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
             }
         };
         fetch(0);
-        for (int cg = 0; cg < p.n_cg; ++cg) {
-            const int st = cg & 1;
-            t6_mbar_wait(a_empty + st, ((cg >> 1) & 1) ^ 1);   // first use of each buffer passes at once
+        for (int cg = 0; cg < p.n_cg; ++cg, ++G) {
+            const int st = G & 1;
+            t6_mbar_wait(a_empty + st, ((G >> 1) & 1) ^ 1);   // first use of each buffer passes at once
             unsigned char* hi = t6sm + L.slab + st * L.slab_stage;
             unsigned char* lo = hi + L.slab_term;
 #pragma unroll
-            for (int i = 0; i < T6_MAXV; ++i) {
+            for (int i = 0; i < NV; ++i) {
                 if (dst[i] < 0) continue;
                 const int off = dst[i] & 0x3FFFFFFF;
                 float h[4], l[4];
@@ -1038,12 +1070,14 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
             asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four producer warps
             if (tid == 0) t6_mbar_arrive(a_full + st);
         }
+        }   // tiles
     } else if (warp == 9) {
         // ================= weight loader: one TMA bulk copy per weight stage =================
         if (lane == 0) {
-            const unsigned char* wbase = reinterpret_cast<const unsigned char*>(p.w6) +
-                                         (size_t)blockIdx.y * p.n_cg * p.K * L.b_tap;
             int it = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const unsigned char* wbase = reinterpret_cast<const unsigned char*>(p.w6) +
+                                         (size_t)((tile / p.t_tiles) % p.n_co) * p.n_cg * p.K * L.b_tap;
             for (int cg = 0; cg < p.n_cg; ++cg)
                 for (int sb = 0; sb < nstage_b; ++sb, ++it) {
                     const int bs = it & 1, k0 = sb * p.TB, ntap = min(p.TB, p.K - k0);
@@ -1052,6 +1086,7 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
                     t6_mbar_expect_tx(b_full + bs, bytes);
                     t6_bulk_g2s(t6sm + L.btile + bs * L.b_stage, wbase + ((size_t)cg * p.K + k0) * L.b_tap, bytes, b_full + bs);
                 }
+            }   // tiles
         }
     } else if (warp == 4) {
         // ================= MMA issuer =================
@@ -1059,11 +1094,12 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T6_M >> 4) << 24);
             const uint32_t lbo_a = (uint32_t)(p.S * p.PL * 16), lbo_b = (uint32_t)N * 16u;
             const uint32_t slab_s = smem_u32_(t6sm + L.slab), btile_s = smem_u32_(t6sm + L.btile);
-            int it = 0;
-            for (int cg = 0; cg < p.n_cg; ++cg) {
-                const int st = cg & 1, acc = cg & 1;
-                t6_mbar_wait(acc_empty + acc, ((cg >> 1) & 1) ^ 1);
-                t6_mbar_wait(a_full + st, (cg >> 1) & 1);
+            int it = 0, G = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+            for (int cg = 0; cg < p.n_cg; ++cg, ++G) {
+                const int st = G & 1, acc = G & 1;
+                t6_mbar_wait(acc_empty + acc, ((G >> 1) & 1) ^ 1);
+                t6_mbar_wait(a_full + st, (G >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem + (uint32_t)(acc * N);
                 uint32_t accumulate = 0;
@@ -1092,13 +1128,16 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
     } else {
         // ================= epilogue warps 5-8: flush partial sums, then bias / residual / store =================
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are the ones this warp may read
+        int G = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int t0 = (tile % p.t_tiles) * T6_M, co0 = ((tile / p.t_tiles) % p.n_co) * N, b = tile / (p.t_tiles * p.n_co);
         const int t = t0 + quarter * 32 + lane;
         float accr[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) accr[j] = 0.f;
-        for (int cg = 0; cg < p.n_cg; ++cg) {
-            const int acc = cg & 1;
-            t6_mbar_wait(acc_full + acc, (cg >> 1) & 1);
+        for (int cg = 0; cg < p.n_cg; ++cg, ++G) {
+            const int acc = G & 1;
+            t6_mbar_wait(acc_full + acc, (G >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int c0 = 0; c0 < N; c0 += 16) {
@@ -1128,19 +1167,24 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
                 }
             }
         }
+        }   // tiles
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * N) : "memory");
 }
 
-template <int N>
+template <int N, int NV>
 static int launch_t6_one(const T6Params& q, int batch, cudaStream_t s) {
     const T6Smem L = t6_smem(N, q.S, q.PL, q.TB);
     ACB_REQUIRE(L.total <= 220 * 1024, "acb_conv1d_t6: tile needs %d B of shared memory", L.total);
-    ACB_CHECK_CUDA(cudaFuncSetAttribute(conv1d_t6_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    dim3 grid(acb_ceil_div(q.t_out, T6_M), q.c_out / N, batch);
-    conv1d_t6_kernel<N><<<grid, T6_THREADS, (size_t)L.total, s>>>(q);
+    ACB_CHECK_CUDA(cudaFuncSetAttribute(conv1d_t6_kernel<N, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    T6Params r = q;
+    r.t_tiles = acb_ceil_div(q.t_out, T6_M); r.n_co = q.c_out / N; r.n_tiles = r.t_tiles * r.n_co * batch;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    conv1d_t6_kernel<N, NV><<<dim3(min(r.n_tiles, sms)), T6_THREADS, (size_t)L.total, s>>>(r);
     ACB_LAUNCH_CHECK();
     return ACB_OK;
 }
@@ -1163,7 +1207,9 @@ extern "C" int acb_conv1d_t6(const float* x, const float* w6, const float* bias,
     q.TB = kernel < 4 ? kernel : 4;
     ACB_REQUIRE(2 * q.span <= 128 * T6_MAXV, "acb_conv1d_t6: slab too long (%d samples per channel)", q.span);
     cudaStream_t s = (cudaStream_t)stream;
-    return N == 128 ? launch_t6_one<128>(q, batch, s) : launch_t6_one<64>(q, batch, s);
+    const int nv = acb_ceil_div(2 * q.span, 128);
+    if (N == 128) return nv <= 4 ? launch_t6_one<128, 4>(q, batch, s) : (nv <= 12 ? launch_t6_one<128, 12>(q, batch, s) : launch_t6_one<128, 20>(q, batch, s));
+    return nv <= 4 ? launch_t6_one<64, 4>(q, batch, s) : (nv <= 12 ? launch_t6_one<64, 12>(q, batch, s) : launch_t6_one<64, 20>(q, batch, s));
 }
 
 // Few output channels (the decoder's last conv, Cout = audio channels): a thread owns 4 consecutive output steps of
@@ -1193,8 +1239,7 @@ __global__ void __launch_bounds__(256) conv1d_small_cout_kernel(SmallCoParams p)
         __syncthreads();
         for (int cl = warp; cl < nci; cl += 8) {
             const float* xrow = xb + (size_t)(ci0 + cl) * p.t_in;
-            for (int j = lane; j < pitch; j += 32)
-                xs[cl * pitch + j] = j < span ? conv_fetch(xrow, g0 + j, p.t_in, p.t_virt, p.reflect, p.elu) : 0.f;
+            stage_span(xs + cl * pitch, xrow, g0, 1, span, pitch, p.t_in, p.t_virt, p.reflect, p.elu, lane);
         }
         for (int idx = tid; idx < nci * KT * SC_MAXCO; idx += 256) {
             const int c = idx % SC_MAXCO, rk = idx / SC_MAXCO;   // rk = cl*KT + k
