@@ -46,16 +46,6 @@ struct ConvParams {
     int tr_S, tr_trim, tr_tout;   // transposed conv as a GEMM over virtual channels n' = co*S + phase (tcgen05 kernel only)
 };
 
-__device__ __forceinline__ float conv_fetch(const float* __restrict__ xr, int g, int t_in, int t_virt, int reflect,
-                                            int elu) {
-    if (reflect) {
-        if (g < 0) g = -g;
-        if (g >= t_virt) g = 2 * (t_virt - 1) - g;
-    }
-    float v = (g >= 0 && g < t_in) ? xr[g] : 0.f;
-    return elu ? acb_elu(v) : v;
-}
-
 // One warp stages dst[q] = act(x[g0 + q * gstep]) for q in [0, n) (zero beyond, up to n_store): the global loads of 8 lane-strided
 // entries are requested before the first is consumed.  A plain `dst[j] = act(load(j))` loop is a chain of dependent L2 round trips
 // (the activation branches on the loaded value and the compiler cannot move a load above the shared-memory store before it): that
@@ -892,8 +882,9 @@ static int launch_conv1d_t5(const ConvParams& p, int batch, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (round-2 candidate; written without GPU time left in round 1 -> NOT validated on hardware, not used by
-// EncodecModel; reachable only through acb_conv1d_t6 and a GPU test that is skipped unless ACB_TEST_EXPERIMENTAL=1).
+// Written at the end of round 1 without GPU time; validated on B200 in round 2 (every test green on first contact) and since then the
+// encoder's kernel for k > 1 with >= 128 output channels (EncodecModel encoder_precision='fp32_tc').  Round-2 changes, each from an ncu
+// capture: raw input samples through a cp.async ring instead of one vector at a time, and the CTA persistent over tiles.
 //
 // conv1d_t6: implicit-GEMM convolution on tcgen05 WITHOUT an im2col tile, warp-specialised and double-buffered, with
 // the TMEM accumulator flushed into fp32 registers once per 8-channel group.  It answers the two measured problems of
@@ -947,8 +938,9 @@ __device__ __forceinline__ void t6_bulk_g2s(void* dst, const void* src, uint32_t
 }
 
 // shared-memory layout (bytes), shared by kernel and launcher
-struct T6Smem { int slab_term, slab_stage, b_tap, b_stage, slab, btile, bars, total; };
-__host__ __device__ inline T6Smem t6_smem(int N, int S, int PL, int TB) {
+struct T6Smem { int slab_term, slab_stage, b_tap, b_stage, slab, btile, bars, raw, raw_stage, total; };
+constexpr int T6_RAW_DEPTH = 3;   // channel groups of raw input in flight per CTA (cp.async ring), kernels with <= 12 vectors per thread
+__host__ __device__ inline T6Smem t6_smem(int N, int S, int PL, int TB, int NV) {
     T6Smem L;
     L.slab_term = 2 * S * PL * 16;          // [c(2)][phase][row][4 floats]
     L.slab_stage = 2 * L.slab_term;         // hi, lo
@@ -957,7 +949,9 @@ __host__ __device__ inline T6Smem t6_smem(int N, int S, int PL, int TB) {
     L.slab = 0;
     L.btile = 2 * L.slab_stage;
     L.bars = L.btile + 2 * L.b_stage;
-    L.total = L.bars + 12 * 8 + 16;
+    L.raw = L.bars + 12 * 8 + 16;           // [T6_RAW_DEPTH][NV][4 channels][128 threads] raw samples (NV <= 12 only)
+    L.raw_stage = NV <= 12 ? NV * 4 * 128 * 4 : 0;
+    L.total = L.raw + T6_RAW_DEPTH * L.raw_stage;
     return L;
 }
 
@@ -966,7 +960,7 @@ __host__ __device__ inline T6Smem t6_smem(int N, int S, int PL, int TB) {
 template <int N, int NV>
 __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
     extern __shared__ __align__(128) unsigned char t6sm[];
-    const T6Smem L = t6_smem(N, p.S, p.PL, p.TB);
+    const T6Smem L = t6_smem(N, p.S, p.PL, p.TB, NV);
     uint64_t* bars = reinterpret_cast<uint64_t*>(t6sm + L.bars);
     uint64_t* a_full = bars;          // [2] slab staged            (1 arrival: elected producer)
     uint64_t* a_empty = bars + 2;     // [2] slab consumed          (tcgen05.commit)
@@ -1017,6 +1011,76 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
             }
         }
         int G = 0;   // running channel-group counter (slab buffer = G & 1)
+        if constexpr (NV <= 12) {
+        // ---- raw samples through a cp.async ring, T6_RAW_DEPTH channel groups deep.  The input streams from HBM (every sample is used by
+        //      two tiles at most): with one register batch per group in flight an SM had ~16 KB outstanding against ~2 us of latency --
+        //      0.8 TB/s over the chip, 38 % of all stall samples on the first use of the batch (profiles/r2_ncu_conv1d_t6_persistent_*).
+        //      The ring keeps 3 groups (~50 KB) in flight, costs no registers, and runs across tile boundaries.
+        float* rawsm = reinterpret_cast<float*>(t6sm + L.raw);
+        const int raw_stage = NV * 4 * 128;
+        int itile = blockIdx.x, icg = 0, islot = 0;
+        auto issue = [&]() {
+            if (itile < p.n_tiles) {
+                const int it0 = (itile % p.t_tiles) * T6_M, ib = itile / (p.t_tiles * p.n_co);
+                const int ig0 = it0 * p.S - p.pad_left;
+                const float* ixb = p.x + ((size_t)ib * p.c_in + (size_t)icg * 8) * p.t_in;
+                const uint32_t rs = smem_u32_(rawsm + islot * raw_stage + tid);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    if (dst[i] >= 0) {
+                        int g = ig0 + jj[i];
+                        if (p.reflect) {
+                            if (g < 0) g = -g;
+                            if (g >= p.t_virt) g = 2 * (p.t_virt - 1) - g;
+                        }
+                        const bool ok = g >= 0 && g < p.t_in;
+                        const float* sp = ixb + (size_t)(((dst[i] >> 30) & 1) * 4) * p.t_in + (ok ? g : 0);
+                        const uint32_t nbytes = ok ? 4u : 0u;   // 0: zero-fill (padding)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(rs + (uint32_t)((i * 4 + q) * 128 * 4)),
+                                         "l"(sp + (size_t)q * p.t_in), "r"(nbytes) : "memory");
+                    }
+                }
+                if (++icg == p.n_cg) { icg = 0; itile += gridDim.x; }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            islot = islot + 1 == T6_RAW_DEPTH ? 0 : islot + 1;
+        };
+#pragma unroll 1
+        for (int d = 0; d < T6_RAW_DEPTH; ++d) issue();
+        int cslot = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+        for (int cg = 0; cg < p.n_cg; ++cg, ++G) {
+            const int st = G & 1;
+            asm volatile("cp.async.wait_group %0;" ::"n"(T6_RAW_DEPTH - 1) : "memory");   // this thread's copies of the oldest group have landed
+            t6_mbar_wait(a_empty + st, ((G >> 1) & 1) ^ 1);   // first use of each buffer passes at once
+            unsigned char* hi = t6sm + L.slab + st * L.slab_stage;
+            unsigned char* lo = hi + L.slab_term;
+            const float* rw = rawsm + cslot * raw_stage + tid;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                if (dst[i] < 0) continue;
+                const int off = dst[i] & 0x3FFFFFFF;
+                float h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float r = rw[(i * 4 + q) * 128];
+                    const float v = p.elu ? acb_elu(r) : r;
+                    h[q] = __uint_as_float(to_tf32(v));
+                    l[q] = __uint_as_float(to_tf32(v - h[q]));
+                }
+                *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+            issue();   // refill the slot just consumed (islot == cslot here)
+            cslot = cslot + 1 == T6_RAW_DEPTH ? 0 : cslot + 1;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+            asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four producer warps
+            if (tid == 0) t6_mbar_arrive(a_full + st);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int t0 = (tile % p.t_tiles) * T6_M, b = tile / (p.t_tiles * p.n_co);
         const int g0 = t0 * p.S - p.pad_left;
@@ -1071,6 +1135,7 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
             if (tid == 0) t6_mbar_arrive(a_full + st);
         }
         }   // tiles
+        }   // register path (NV > 12)
     } else if (warp == 9) {
         // ================= weight loader: one TMA bulk copy per weight stage =================
         if (lane == 0) {
@@ -1176,8 +1241,8 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
 
 template <int N, int NV>
 static int launch_t6_one(const T6Params& q, int batch, cudaStream_t s) {
-    const T6Smem L = t6_smem(N, q.S, q.PL, q.TB);
-    ACB_REQUIRE(L.total <= 220 * 1024, "acb_conv1d_t6: tile needs %d B of shared memory", L.total);
+    const T6Smem L = t6_smem(N, q.S, q.PL, q.TB, NV);
+    ACB_REQUIRE(L.total <= 227 * 1024, "acb_conv1d_t6: tile needs %d B of shared memory", L.total);
     ACB_CHECK_CUDA(cudaFuncSetAttribute(conv1d_t6_kernel<N, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     T6Params r = q;
     r.t_tiles = acb_ceil_div(q.t_out, T6_M); r.n_co = q.c_out / N; r.n_tiles = r.t_tiles * r.n_co * batch;

@@ -4,18 +4,20 @@
 // (lm.py:393-418) + the delay-pattern write-back (lm.py:553-562), replayed as ONE CUDA graph per step with every
 // step-dependent quantity (position, tokens) resident on the device.
 //
-// The step is HBM-bound: all layer weights (fp16, 3.65 GB for medium) and the KV cache are read once per step and
-// arithmetic intensity is ~rows FLOP/B.  Design consequences:
-//   * weights stay in the reference's [out][in] fp16 layout and stream straight from HBM into tensor-core
-//     fragments (ld.global.nc.L1::no_allocate 128-bit), never through shared memory: a 16x32 block of W is the
-//     A operand of two m16n8k16 MMAs, the activations (a few KB, L1/L2 resident) are the B operand, so the tile
-//     is 16 output features x (8*NT) rows and nothing is wasted on padding rows up to 128.
-//   * every GEMM spreads its weight matrix over >= 2 CTAs per SM; small-N GEMMs split K across CTAs and the
-//     partial sums are reduced (in a fixed order: bit-reproducible) by the consumer kernel, which is the residual
-//     add + LayerNorm, so that reduction costs no extra pass.
-//   * K/V go from the QKV GEMM epilogue straight into the cache; cross-attention K/V are computed once per
-//     generate() instead of every step (the reference recomputes them, transformer.py:355-357).
-//   * attention for one query token: one CTA per (row, head) streaming K then V with 128-bit loads.
+// The step is HBM-bound in bytes (all layer weights, fp16, 3.2 GB for medium, and the KV cache are read once per step at ~rows FLOP/B)
+// and LATENCY-bound in time: 11 dependent kernels per layer.  Design consequences:
+//   * weights stay in the reference's [out][in] fp16 layout; a CTA's 16 (or 32) x kslice slab is fetched with TMA bulk copies BEFORE
+//     griddepcontrol.wait, i.e. while the previous kernel of the graph still runs (programmatic dependent launch); a 16x32 block of W
+//     is the A operand of two m16n8k16 MMAs, the activations (a few KB, L2 resident) are the B operand, so the tile is 16 output
+//     features x (8*NT) rows and nothing is wasted on padding rows up to 128.
+//   * every GEMM spreads its weight matrix over >= 2 CTAs per SM; small-N GEMMs split K across CTAs and the partial sums are reduced
+//     (in a fixed order: bit-reproducible) by the consumer kernel, which is the residual add + LayerNorm, so that reduction costs no
+//     extra pass.
+//   * K/V go from the QKV GEMM epilogue straight into the cache; cross-attention K/V are computed once per generate() instead of
+//     every step (the reference recomputes them, transformer.py:355-357).
+//   * attention for one query token: one CTA per (row, head) streaming K and V through a cp.async ring (lm_attn2_kernel).
+// Alternatives that were built and measured slower (persistent fused step, cluster split-K with LayerNorm on load, chain kernels, ...)
+// are listed with their numbers in DESIGN.md section 3.1.
 #include "common.cuh"
 #include "lm_step.cuh"
 #include <math.h>
@@ -509,6 +511,129 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn_kernel(AttnParams p) {
     tl_stamp(p.timing, 3);
 }
 
+// Self attention for one query token, deep-prefetch variant (the default decode path since round 2; ACB_LM_ATTN=v1 keeps the kernel
+// above, which also serves prefill and split-KV).  Same work split and arithmetic as lm_attn_kernel<false>: CTA = (row, head), 8 warps,
+// a warp instruction covers 4 consecutive cache positions, 8 lanes share a position.  What changes is how K and V get there: every lane
+// copies its 16-byte slices with cp.async into a private slot of a per-warp shared-memory ring, ATT2_DEPTH iterations deep, and reads
+// them back (its own 32 bytes) one iteration at a time.  With register loads a lane had 128 bytes in flight in bursts (4 iterations
+// requested, then all consumed): ~83 KB per SM at 2.6 CTAs per SM, against the ~13 MB that 6.5 TB/s x ~2 us of loaded HBM latency asks
+// of the chip (88 KB per SM): 4.05 TB/s at KV 751.  The ring keeps up to 8 x 32 bytes per lane outstanding continuously, in shared
+// memory instead of registers.
+constexpr int ATT2_DEPTH = 8;
+__global__ void __launch_bounds__(ATT_WARPS * 32) lm_attn2_kernel(AttnParams p) {
+    extern __shared__ __align__(16) unsigned char att2sm[];   // [warp][depth][K | V][32 lanes][16 B]
+    __shared__ float wm[ATT_WARPS], wl[ATT_WARPS], wacc[ATT_WARPS][64];
+    const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = blockIdx.y;
+    const int sl = lane & 7, pg = lane >> 3;
+    tl_stamp(p.timing, 0);
+    pdl_trigger();
+    pdl_wait();
+    tl_stamp(p.timing, 1);
+    const int n = p.fixed_len > 0 ? p.fixed_len : p.pos[0] + 1;
+    const size_t base = ((size_t)row * p.H + h) * p.cache_len * 64 + sl * 8;
+    const __half* kb = p.kc + base;
+    const __half* vb = p.vc + base;
+    const uint32_t ring = smem_u32(att2sm) + (uint32_t)(warp * ATT2_DEPTH * 1024 + lane * 16);
+    // iteration k of this warp covers positions (k * 8 + warp) * 4 + pg
+    const int n_it = (n + 31 - warp * 4) / 32 > 0 ? (n - warp * 4 + 31) / 32 : 0;   // iterations with at least one live position group
+    auto issue = [&](int k) {
+        if (k < n_it) {
+            const int pp = (k * ATT_WARPS + warp) * 4 + pg;
+            if (pp < n) {
+                const uint32_t d = ring + (uint32_t)((k % ATT2_DEPTH) * 1024);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(kb + (size_t)pp * 64) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u), "l"(vb + (size_t)pp * 64) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int k = 0; k < ATT2_DEPTH - 1; ++k) issue(k);
+
+    float q[8];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(p.q + (size_t)row * p.d + h * 64 + sl * 8);
+        const float4 qa = qp[0], qb = qp[1];
+        q[0] = half_round(qa.x) * p.scale; q[1] = half_round(qa.y) * p.scale; q[2] = half_round(qa.z) * p.scale;
+        q[3] = half_round(qa.w) * p.scale; q[4] = half_round(qb.x) * p.scale; q[5] = half_round(qb.y) * p.scale;
+        q[6] = half_round(qb.z) * p.scale; q[7] = half_round(qb.w) * p.scale;
+    }
+    tl_stamp(p.timing, 4);
+    OnlineSM st;
+    st.m = -INFINITY; st.l = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) st.acc[e] = 0.f;
+
+    for (int k = 0; k < n_it; ++k) {                 // warp-uniform trip count (the shuffles need all 32 lanes)
+        issue(k + ATT2_DEPTH - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(ATT2_DEPTH - 1) : "memory");   // iteration k's copies of this lane have landed
+        const int pp = (k * ATT_WARPS + warp) * 4 + pg;
+        const uint32_t sa = ring + (uint32_t)((k % ATT2_DEPTH) * 1024);
+        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (pp < n) {
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(kv.x), "=r"(kv.y), "=r"(kv.z), "=r"(kv.w) : "r"(sa));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(vv.x), "=r"(vv.y), "=r"(vv.z), "=r"(vv.w) : "r"(sa + 512u));
+        }
+        const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(k2[e]);
+            s = fmaf(q[2 * e], f.x, s);
+            s = fmaf(q[2 * e + 1], f.y, s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (pp < n) {
+            const float mn = fmaxf(st.m, s);
+            const float corr = __expf(st.m - mn);   // exp(-inf) = 0 on the first position
+            const float pw = __expf(s - mn);
+            st.l = st.l * corr + pw;
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(v2[e]);
+                st.acc[2 * e] = fmaf(pw, f.x, st.acc[2 * e] * corr);
+                st.acc[2 * e + 1] = fmaf(pw, f.y, st.acc[2 * e + 1] * corr);
+            }
+            st.m = mn;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    tl_stamp(p.timing, 2);
+    // merge the 4 position groups of the warp, then the warps (as lm_attn_kernel)
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, st.m, o), l2 = __shfl_xor_sync(0xffffffffu, st.l, o);
+        float a2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a2[e] = __shfl_xor_sync(0xffffffffu, st.acc[e], o);
+        osm_merge(st, m2, l2, a2);
+    }
+    if (pg == 0) {
+        if (sl == 0) { wm[warp] = st.m; wl[warp] = st.l; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) wacc[warp][sl * 8 + e] = st.acc[e];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float mx = wm[0];
+#pragma unroll
+        for (int w = 1; w < ATT_WARPS; ++w) mx = fmaxf(mx, wm[w]);
+        float l = 0.f, o = 0.f;
+#pragma unroll
+        for (int w = 0; w < ATT_WARPS; ++w) {
+            const float cw = wm[w] == -INFINITY ? 0.f : __expf(wm[w] - mx);
+            l = fmaf(wl[w], cw, l);
+            o = fmaf(wacc[w][tid], cw, o);
+        }
+        p.out[(size_t)row * p.d + h * 64 + tid] = __float2half_rn(o / l);
+    }
+    tl_stamp(p.timing, 3);
+}
+
 // Cross attention over the (short) text condition: one WARP per (row, head), lane = text position for the scores,
 // lane = 2 output dims for the weighted sum.  K/V were computed once per generate() (acb_lm_begin).
 template <bool PF>
@@ -797,6 +922,7 @@ struct acb_lm {
     int launches = 0;
     bool has_cross = false;
     bool pdl = true;          // programmatic dependent launch between the kernels of a step
+    bool attn2 = true;        // deep-prefetch self attention (cp.async ring); ACB_LM_ATTN=v1: register loads
     bool fused = false;       // ACB_LM_STEP=fused / rotary positions: the whole transformer of a step is ONE persistent kernel (lm_step.cu)
     StepLaunch step{};
     unsigned long long* trace = nullptr;   // ACB_LM_STEP_TRACE=1: per-phase %globaltimer stamps of CTA 0
@@ -1029,6 +1155,8 @@ static int enqueue_step_kernels(acb_lm* lm, cudaStream_t s, float* logits_out, i
             a.split_min = max(129, env_int("ACB_LM_ATT_SPLIT_MIN", 768));
             a.rows_real = rows_real;
             if (pf) ACB_LAUNCH((lm_attn_kernel<false, true>), dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
+            else if (att_split <= 1 && lm->attn2)
+                ACB_LAUNCH(lm_attn2_kernel, dim3(H, rows), dim3(ATT_WARPS * 32), (size_t)ATT_WARPS * ATT2_DEPTH * 1024, s, pdl, a);
             else if (att_split > 1) ACB_LAUNCH(lm_attn_kernel<true>, dim3(H, rows, att_split), dim3(ATT_WARPS * 32), 0, s, pdl, a);
             else ACB_LAUNCH(lm_attn_kernel<false>, dim3(H, rows), dim3(ATT_WARPS * 32), 0, s, pdl, a);
             ++nl;
@@ -1152,6 +1280,8 @@ extern "C" int acb_lm_create(const acb_lm_config* cfg, const acb_lm_weights* w, 
     if (ea == cudaSuccess) ea = gemm_attr_all<EPI_QKV_PF>();
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_WARPS * ATT2_DEPTH * 1024);
+    if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_attn2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_cross_attn_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_ln_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (ea == cudaSuccess) ea = cudaFuncSetAttribute(lm_embed_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1233,6 +1363,10 @@ extern "C" int acb_lm_begin(acb_lm_t* lm, const float* cross, int batch, int row
         if (env_int("ACB_LM_TIMING", 0) && !lm->timing) {
             ACB_CHECK_CUDA(cudaMalloc(&lm->timing, (size_t)ACB_TIMING_MAX_GEMMS * ACB_TIMING_MAX_CTAS * 64));
             ACB_CHECK_CUDA(cudaMemset(lm->timing, 0, (size_t)ACB_TIMING_MAX_GEMMS * ACB_TIMING_MAX_CTAS * 64));
+        }
+        {
+            const char* ea = getenv("ACB_LM_ATTN");
+            lm->attn2 = !(ea && ea[0] == 'v' && ea[1] == '1');
         }
         const char* ev = getenv("ACB_LM_STEP");
         // The persistent fused step (lm_step.cu; needs the packed weights) is OPT-IN: ACB_LM_STEP=fused, or a model with rotary
