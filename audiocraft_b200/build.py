@@ -21,6 +21,12 @@ FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=s
 if os.environ.get('ACB_STEP_NCW'):   # experiment: compute warps per CTA of the fused decode step (csrc/lm_step.cu)
     FLAGS.append('-DACB_STEP_NCW=' + os.environ['ACB_STEP_NCW'])
 OBJ_SUFFIX = '.o'
+if os.environ.get('ACB_BUILD_VARIANT'):   # experiment builds: extra -D flags (ACB_BUILD_DEFS) into libaudiocraft_b200_<variant>.so; run with ACB_LIB=<path>
+    _v = os.environ['ACB_BUILD_VARIANT']
+    FLAGS += os.environ.get('ACB_BUILD_DEFS', '').split()
+    LIB = os.path.join(HERE, f'libaudiocraft_b200_{_v}.so')
+    STAMP = LIB + '.stamp'
+    OBJ_SUFFIX = f'.{_v}.o'
 if os.environ.get('ACB_BUILD_TIMELINE') == '1':   # instrumented build: in-kernel %globaltimer stamps (see csrc/lm.cu tl_stamp)
     FLAGS.append('-DACB_TIMELINE')               # goes to its own file (never the product library): run with ACB_LIB=<that path>
     LIB = os.path.join(HERE, 'libaudiocraft_b200_timeline.so')

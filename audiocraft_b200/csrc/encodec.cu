@@ -1272,7 +1272,10 @@ extern "C" int acb_conv1d_t6(const float* x, const float* w6, const float* bias,
     q.TB = kernel < 4 ? kernel : 4;
     ACB_REQUIRE(2 * q.span <= 128 * T6_MAXV, "acb_conv1d_t6: slab too long (%d samples per channel)", q.span);
     cudaStream_t s = (cudaStream_t)stream;
-    const int nv = acb_ceil_div(2 * q.span, 128);
+    int nv = acb_ceil_div(2 * q.span, 128);
+    // the cp.async ring of the <= 12-vector kernels needs 3 x nv_class x 2 KB on top of slab and weight stages: where that does not fit
+    // (long slabs x wide strides), the register-prefetch kernel takes the layer
+    if (nv <= 12 && t6_smem(N, q.S, q.PL, q.TB, nv <= 4 ? 4 : 12).total > 227 * 1024) nv = 20;
     if (N == 128) return nv <= 4 ? launch_t6_one<128, 4>(q, batch, s) : (nv <= 12 ? launch_t6_one<128, 12>(q, batch, s) : launch_t6_one<128, 20>(q, batch, s));
     return nv <= 4 ? launch_t6_one<64, 4>(q, batch, s) : (nv <= 12 ? launch_t6_one<64, 12>(q, batch, s) : launch_t6_one<64, 20>(q, batch, s));
 }
@@ -1699,7 +1702,9 @@ __global__ void __launch_bounds__(LTC_NW * 32, 1) lstm_tc_kernel(LstmParams p) {
             const float4* hf4 = reinterpret_cast<const float4*>(hprev);
             // B fragments are requested LTC_PB k-steps at a time.  Measured per LSTM block (2 layers x 500 steps, H = 1024, 32 items):
             // 8 warps x 4 k-steps 14.5 ms; 8 warps, all 16 k-steps up front (255 registers) 16.1 ms; 16 warps x all 8 k-steps (128
-            // registers, spills) 17.2 ms; fp32 FMA kernel 18.3 ms (profiles/r2_perf_encodec_v3*.log, v4*.log).
+            // registers, spills) 17.2 ms; two alternating 16-item halves with their own barriers (barrier and h round trip off the
+            // critical path, but the W_hh split done twice per step) 16.0 ms; fp32 FMA kernel 18.3 ms (profiles/r2_perf_encodec_v3*.log,
+            // v4*.log, v8*.log).  ncu: issue-latency bound (two warps per scheduler, 32 % of the stall samples `wait`, 5 % `math`).
 #pragma unroll 1
             for (int s0 = 0; s0 < ksteps; s0 += LTC_PB) {
                 float4 b0[LTC_PB], b1[LTC_PB];

@@ -210,7 +210,10 @@ struct GemmParams {
 // activation reads per 14 MB weight matrix; ~0.8 us per dependent batch of loads).
 template <int NT, int EPI, int FT2 = 1>
 __global__ void __launch_bounds__(128) lm_gemm_kernel(GemmParams p) {
-    constexpr int U = NT <= 2 ? 4 : (NT <= 4 ? 2 : 1);
+#ifndef ACB_GEMM_U2
+#define ACB_GEMM_U2 4   // k-blocks per batch of activation loads at <= 16 rows (experiment builds: -DACB_GEMM_U2=6)
+#endif
+    constexpr int U = NT <= 2 ? ACB_GEMM_U2 : (NT <= 4 ? 2 : 1);
     constexpr int RP = 8 * NT + 1;
     constexpr int FB = 16 * FT2;                     // output features per CTA
     extern __shared__ __align__(128) unsigned char gsm[];

@@ -23,7 +23,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), name
     assert L.acb_version() >= 100
     assert L.acb_lm_rows_pad(1) == 16 and L.acb_lm_rows_pad(16) == 16 and L.acb_lm_rows_pad(17) == 32 and L.acb_lm_rows_pad(64) == 64
-    assert L.acb_lstm_state_bytes(2, 8) == (2 * 2 * 8 + 64) * 4
+    assert L.acb_lstm_state_bytes(2, 8) == (2 * 32 * 8 + 64) * 4      # h double buffer for max(batch, 32) item slots + barrier counters
+    assert L.acb_lstm_state_bytes(40, 8) == (2 * 40 * 8 + 64) * 4
 
 
 def test_sass_is_sm100a():
