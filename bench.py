@@ -407,7 +407,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         enc_ms = e0.elapsed_time(e1) / 3
         secondary = dict(metric='EnCodec 32kHz encode+decode MSamples/sec', value=round(xb.numel() / (enc_ms / 1e3) / 1e6, 2),
-                         unit='MSamples/s', config='32 x 10 s mono per GPU; encoder fp32-accurate (tcgen05 3xTF32 with fp32 flushes where it wins, fp32 FMA elsewhere: index-exact), decoder 3xTF32 on tcgen05',
+                         unit='MSamples/s', config='32 x 10 s mono per GPU; encoder fp32-accurate and index-exact (3xTF32 with bounded tensor-core accumulation runs: conv1d_t6 on tcgen05, fused residual blocks and the LSTM step on mma.sync; fp32 FMA where neither wins), decoder 3xTF32 (tcgen05 convolutions, fused residual blocks)',
                          ms=round(enc_ms, 2), roofline=encodec_roofline(xb.numel(), enc_ms))
         # throughput mode: the encoder's convolutions on the tensor cores as well (latents within 1.5e-4 of fp32)
         from audiocraft_b200 import synth as _synth

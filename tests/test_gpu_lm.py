@@ -421,6 +421,21 @@ def test_fused_step_matches_per_phase_kernels(monkeypatch, name, B):
     assert (out_f == out_b).float().mean() > 0.9
 
 
+@pytest.mark.parametrize('name,B,T', [('lm_mini', 3, 70), ('lm_medium_2l', 8, 300)])
+def test_cp_async_attention_is_bit_identical_to_register_loads(monkeypatch, name, B, T):
+    """lm_attn2_kernel (K / V through a per-warp cp.async ring, the decode default) visits the cache positions in the same per-lane order
+    and merges them with the same tree as lm_attn_kernel (register loads, ACB_LM_ATTN=v1): the logits must be bit-identical, over
+    contexts long enough to wrap the 8-deep ring many times (T > 32 x 8 positions)."""
+    cfg, sd, m = _model(name, 5)
+    _, _, cross = H.lm_condition(cfg, sd, B, 5, 1)
+    seq = torch.randint(0, cfg['card'], (B, 4, T + 4), generator=torch.Generator().manual_seed(2))
+    keep = [0, 1, 31, 32, 33, T // 2, T - 2, T - 1]
+    a = m.teacher_forced_logits(seq, cross, 3.0, n_steps=T, keep=keep).cpu()
+    monkeypatch.setenv('ACB_LM_ATTN', 'v1')
+    b = m.teacher_forced_logits(seq, cross, 3.0, n_steps=T, keep=keep).cpu()
+    assert torch.equal(a, b), f'max diff {(a - b).abs().max():.3e}'
+
+
 @pytest.mark.parametrize('name,B,T0', [('lm_mini', 2, 9), ('lm_mini', 5, 23), ('lm_medium_2l', 8, 21)])
 def test_prompt_prefill_equals_token_by_token(monkeypatch, name, B, T0):
     """Prompt prefill (acb_lm_prefill = the reference's multi-token first call, lm.py:513-534, transformer.py:240-247): 64 / rows
