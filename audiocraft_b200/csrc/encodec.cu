@@ -178,11 +178,22 @@ static int launch_conv1d(const ConvParams& p, int batch, cudaStream_t s) {
 // row-offset table, i.e. the im2col matrix is never materialised.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32_(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// fp32 -> tf32, round to nearest, ties away from zero (= cvt.rna.tf32.f32 for every finite input): add half an ulp of the 10-bit
+// mantissa to the magnitude bits and clear the 13 dropped bits.  Two integer instructions; the cvt instruction itself is emulated in
+// SASS with ~5 (bias add, mask, NaN test + select), and every 3xTF32 operand costs two conversions, so in the mma.sync kernels the
+// operand split was ~11 instructions per element against 3 MMAs (lstm_tc_kernel: 96 HMMA among ~900 instructions per 4 k-steps).
+// -DACB_CVT_TF32 restores the instruction (NaN payloads are the only difference).
+#ifdef ACB_CVT_TF32
 __device__ __forceinline__ uint32_t to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return r;
 }
+#else
+__device__ __forceinline__ uint32_t to_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
+#endif
+// (Handing the low term x - hi to the tensor core unrounded -- it reads only the upper 19 bits of a tf32 operand -- saves two more
+//  instructions per element and measured no faster: 84.63 vs 84.74 ms for the codec, profiles/r2_perf_encodec_v12*.  Not kept.)
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
