@@ -7,6 +7,7 @@
 // of every activation per layer), weight-norm is folded once at load, the [frames x bins] VQ distance
 // matrix never leaves the SM, and the LSTM keeps W_hh resident in the 227 KB shared memory of 128 SMs.
 #include "common.cuh"
+#include "gridbar.cuh"
 #include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
@@ -355,7 +356,8 @@ __global__ void __launch_bounds__(HD >= 128 ? 512 : 256, HD >= 128 ? 1 : 2) resb
     constexpr bool EARLY_SKIP = !FLUSH || HD == 32;
     constexpr bool PF_W2 = !(FLUSH && HD == 64);      // next W2 chunk prefetched into registers during the MMAs (registers permitting)   // skip-connection loads before the MMAs of a pass (registers permitting) or after
     constexpr int WHALF = (3 * RB_CH * WP1) > (HD * WP2) ? (3 * RB_CH * WP1) : (HD * WP2);
-    constexpr int NSL = C * RB_XSP / NTHR, SLB = 17;   // slab elements per thread (34 / 68 / 136), requested 17 at a time
+    constexpr int NSL = C * RB_XSP / NTHR, SLB = 34;   // slab elements per thread (34 / 68 / 68), requested 34 at a time (ncu: 21 % of the
+                                                       // stall samples were the first use of a 17-element batch, twice per tile at 64 channels)
     constexpr int NW1 = 3 * RB_CH * HD / NTHR;         // W1 chunk elements per thread (6 / 12 / 24)
     constexpr int NW2 = HD * 64 / NTHR;                // W2 chunk elements per thread (8 / 16 / 32)
     static_assert(NSL % SLB == 0 && C * RB_XSP % NTHR == 0, "slab staging");
@@ -922,6 +924,7 @@ struct T6Params {
     int c_in, c_out, t_in, t_virt, t_out, K, S, D, pad_left, reflect, elu;
     int span, PL, n_cg, TB;   // slab length, rows per phase plane, 8-channel groups, taps per weight stage
     int t_tiles, n_co, n_tiles;   // persistent tile loop: tile -> (time tile, output-channel tile, item)
+    int raw_vec;                  // slab vectors per staging thread in use (<= NV)
 };
 
 __device__ __forceinline__ void t6_mbar_init(uint64_t* b, uint32_t count) {
@@ -950,8 +953,9 @@ __device__ __forceinline__ void t6_bulk_g2s(void* dst, const void* src, uint32_t
 
 // shared-memory layout (bytes), shared by kernel and launcher
 struct T6Smem { int slab_term, slab_stage, b_tap, b_stage, slab, btile, bars, raw, raw_stage, total; };
-constexpr int T6_RAW_DEPTH = 3;   // channel groups of raw input in flight per CTA (cp.async ring), kernels with <= 12 vectors per thread
-__host__ __device__ inline T6Smem t6_smem(int N, int S, int PL, int TB, int NV) {
+// raw_vec = slab vectors per staging thread actually used (ceil(2 span / 128)), raw_depth = channel groups of raw input in flight per CTA
+// (cp.async ring; 0 = the register-prefetch kernel)
+__host__ __device__ inline T6Smem t6_smem(int N, int S, int PL, int TB, int raw_vec, int raw_depth) {
     T6Smem L;
     L.slab_term = 2 * S * PL * 16;          // [c(2)][phase][row][4 floats]
     L.slab_stage = 2 * L.slab_term;         // hi, lo
@@ -960,18 +964,18 @@ __host__ __device__ inline T6Smem t6_smem(int N, int S, int PL, int TB, int NV) 
     L.slab = 0;
     L.btile = 2 * L.slab_stage;
     L.bars = L.btile + 2 * L.b_stage;
-    L.raw = L.bars + 12 * 8 + 16;           // [T6_RAW_DEPTH][NV][4 channels][128 threads] raw samples (NV <= 12 only)
-    L.raw_stage = NV <= 12 ? NV * 4 * 128 * 4 : 0;
-    L.total = L.raw + T6_RAW_DEPTH * L.raw_stage;
+    L.raw = L.bars + 12 * 8 + 16;           // [DEPTH][NV][4 channels][128 threads] raw samples (NV <= 12 only)
+    L.raw_stage = raw_vec * 4 * 128 * 4;
+    L.total = L.raw + raw_depth * L.raw_stage;
     return L;
 }
 
 // NV = slab vectors per staging thread (4 / 12 / 20): the maps and the prefetched raw samples live in registers, and 10 warps are allocated
 // as 12 (warp allocation granularity 4), which caps the kernel at 168 registers per thread.
-template <int N, int NV>
+template <int N, int NV, int DEPTH>   // DEPTH: cp.async ring depth (0: register prefetch)
 __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
     extern __shared__ __align__(128) unsigned char t6sm[];
-    const T6Smem L = t6_smem(N, p.S, p.PL, p.TB, NV);
+    const T6Smem L = t6_smem(N, p.S, p.PL, p.TB, p.raw_vec, DEPTH);
     uint64_t* bars = reinterpret_cast<uint64_t*>(t6sm + L.bars);
     uint64_t* a_full = bars;          // [2] slab staged            (1 arrival: elected producer)
     uint64_t* a_empty = bars + 2;     // [2] slab consumed          (tcgen05.commit)
@@ -1022,13 +1026,13 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
             }
         }
         int G = 0;   // running channel-group counter (slab buffer = G & 1)
-        if constexpr (NV <= 12) {
-        // ---- raw samples through a cp.async ring, T6_RAW_DEPTH channel groups deep.  The input streams from HBM (every sample is used by
+        if constexpr (DEPTH > 0) {
+        // ---- raw samples through a cp.async ring, DEPTH channel groups deep.  The input streams from HBM (every sample is used by
         //      two tiles at most): with one register batch per group in flight an SM had ~16 KB outstanding against ~2 us of latency --
         //      0.8 TB/s over the chip, 38 % of all stall samples on the first use of the batch (profiles/r2_ncu_conv1d_t6_persistent_*).
-        //      The ring keeps 3 groups (~50 KB) in flight, costs no registers, and runs across tile boundaries.
+        //      The ring keeps 3-4 groups (50-70 KB) in flight, costs no registers, and runs across tile boundaries.
         float* rawsm = reinterpret_cast<float*>(t6sm + L.raw);
-        const int raw_stage = NV * 4 * 128;
+        const int raw_stage = p.raw_vec * 4 * 128;
         int itile = blockIdx.x, icg = 0, islot = 0;
         auto issue = [&]() {
             if (itile < p.n_tiles) {
@@ -1056,15 +1060,15 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
                 if (++icg == p.n_cg) { icg = 0; itile += gridDim.x; }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            islot = islot + 1 == T6_RAW_DEPTH ? 0 : islot + 1;
+            islot = islot + 1 == DEPTH ? 0 : islot + 1;
         };
 #pragma unroll 1
-        for (int d = 0; d < T6_RAW_DEPTH; ++d) issue();
+        for (int d = 0; d < DEPTH; ++d) issue();
         int cslot = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
         for (int cg = 0; cg < p.n_cg; ++cg, ++G) {
             const int st = G & 1;
-            asm volatile("cp.async.wait_group %0;" ::"n"(T6_RAW_DEPTH - 1) : "memory");   // this thread's copies of the oldest group have landed
+            asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");   // this thread's copies of the oldest group have landed
             t6_mbar_wait(a_empty + st, ((G >> 1) & 1) ^ 1);   // first use of each buffer passes at once
             unsigned char* hi = t6sm + L.slab + st * L.slab_stage;
             unsigned char* lo = hi + L.slab_term;
@@ -1085,7 +1089,7 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
                 *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
             }
             issue();   // refill the slot just consumed (islot == cslot here)
-            cslot = cslot + 1 == T6_RAW_DEPTH ? 0 : cslot + 1;
+            cslot = cslot + 1 == DEPTH ? 0 : cslot + 1;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
             asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four producer warps
             if (tid == 0) t6_mbar_arrive(a_full + st);
@@ -1250,17 +1254,17 @@ __global__ void __launch_bounds__(T6_THREADS, 1) conv1d_t6_kernel(T6Params p) {
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * N) : "memory");
 }
 
-template <int N, int NV>
+template <int N, int NV, int DEPTH>
 static int launch_t6_one(const T6Params& q, int batch, cudaStream_t s) {
-    const T6Smem L = t6_smem(N, q.S, q.PL, q.TB, NV);
+    const T6Smem L = t6_smem(N, q.S, q.PL, q.TB, q.raw_vec, DEPTH);
     ACB_REQUIRE(L.total <= 227 * 1024, "acb_conv1d_t6: tile needs %d B of shared memory", L.total);
-    ACB_CHECK_CUDA(cudaFuncSetAttribute(conv1d_t6_kernel<N, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    ACB_CHECK_CUDA(cudaFuncSetAttribute(conv1d_t6_kernel<N, NV, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     T6Params r = q;
     r.t_tiles = acb_ceil_div(q.t_out, T6_M); r.n_co = q.c_out / N; r.n_tiles = r.t_tiles * r.n_co * batch;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    conv1d_t6_kernel<N, NV><<<dim3(min(r.n_tiles, sms)), T6_THREADS, (size_t)L.total, s>>>(r);
+    conv1d_t6_kernel<N, NV, DEPTH><<<dim3(min(r.n_tiles, sms)), T6_THREADS, (size_t)L.total, s>>>(r);
     ACB_LAUNCH_CHECK();
     return ACB_OK;
 }
@@ -1283,12 +1287,21 @@ extern "C" int acb_conv1d_t6(const float* x, const float* w6, const float* bias,
     q.TB = kernel < 4 ? kernel : 4;
     ACB_REQUIRE(2 * q.span <= 128 * T6_MAXV, "acb_conv1d_t6: slab too long (%d samples per channel)", q.span);
     cudaStream_t s = (cudaStream_t)stream;
-    int nv = acb_ceil_div(2 * q.span, 128);
-    // the cp.async ring of the <= 12-vector kernels needs 3 x nv_class x 2 KB on top of slab and weight stages: where that does not fit
-    // (long slabs x wide strides), the register-prefetch kernel takes the layer
-    if (nv <= 12 && t6_smem(N, q.S, q.PL, q.TB, nv <= 4 ? 4 : 12).total > 227 * 1024) nv = 20;
-    if (N == 128) return nv <= 4 ? launch_t6_one<128, 4>(q, batch, s) : (nv <= 12 ? launch_t6_one<128, 12>(q, batch, s) : launch_t6_one<128, 20>(q, batch, s));
-    return nv <= 4 ? launch_t6_one<64, 4>(q, batch, s) : (nv <= 12 ? launch_t6_one<64, 12>(q, batch, s) : launch_t6_one<64, 20>(q, batch, s));
+    const int nv = acb_ceil_div(2 * q.span, 128);
+    q.raw_vec = nv;
+    // cp.async ring of raw samples, 4 or 3 channel groups deep, where it fits next to the slab and weight stages (227 KB); else the
+    // register-prefetch kernel (long slabs x wide strides, e.g. k = 16, stride 8)
+    const int lim = 227 * 1024;
+    const int depth = nv > 12 ? 0 : (t6_smem(N, q.S, q.PL, q.TB, nv, 4).total <= lim ? 4 : (t6_smem(N, q.S, q.PL, q.TB, nv, 3).total <= lim ? 3 : 0));
+#define ACB_T6_LAUNCH(NN)                                                                                             \
+    do {                                                                                                              \
+        if (depth == 0) return launch_t6_one<NN, 20, 0>(q, batch, s);                                                 \
+        if (nv <= 4) return depth == 4 ? launch_t6_one<NN, 4, 4>(q, batch, s) : launch_t6_one<NN, 4, 3>(q, batch, s); \
+        return depth == 4 ? launch_t6_one<NN, 12, 4>(q, batch, s) : launch_t6_one<NN, 12, 3>(q, batch, s);            \
+    } while (0)
+    if (N == 128) ACB_T6_LAUNCH(128);
+    ACB_T6_LAUNCH(64);
+#undef ACB_T6_LAUNCH
 }
 
 // Few output channels (the decoder's last conv, Cout = audio channels): a thread owns 4 consecutive output steps of
@@ -1784,11 +1797,9 @@ __global__ void __launch_bounds__(LTC_NW * 32, 1) lstm_tc_kernel(LstmParams p) {
         }
         // grid barrier: everyone has published h_t (and is done with the partial-sum buffer) before anyone reads it
         __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(p.bar, 1u);
-            const unsigned target = ncta * (unsigned)(t + 1);
-            while (ld_acquire_u32(p.bar) < target) { }
+        if (tid == 0) {   // release reduction without a return value + acquire polling (csrc/gridbar.cuh): no membar.gl, no atomic round trip
+            gridbar_arrive(p.bar);
+            gridbar_wait(p.bar, ncta * (unsigned)(t + 1));
         }
         __syncthreads();
     }
