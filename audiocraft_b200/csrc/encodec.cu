@@ -1805,6 +1805,175 @@ __global__ void __launch_bounds__(LTC_NW * 32, 1) lstm_tc_kernel(LstmParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Recurrent LSTM step with BOTH operands pre-split into two fp16 terms (hidden % 128 == 0, batch <= 32): the default since the end of
+// round 2.  x = hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 mantissa bits, the precision class of the 3xTF32
+// split (tf32 carries 11), and |W_hh| <~ 1, |h| < 1 sit inside fp16's range (the scaled low terms too).  Then
+//     W h = (hi_w hi_h) + 2^-11 (hi_w lo_h + lo_w hi_h)            [lo lo dropped: 2^-22]
+// is THREE mma.sync.m16n8k16.f16 per 16 reduction elements (the tf32 kernel: six m16n8k8), and -- the actual point -- nothing is
+// converted inside the step any more:
+//   * W_hh's slice is split ONCE, at kernel start, straight into the A-fragment order of its consumer warp:
+//     wfrag[warp][k16 step][m tile][hi | lo][lane][4 x half2], 4 bytes per element like the fp32 copy (128 KB at H = 1024), one
+//     conflict-free LDS.128 per term and m tile;
+//   * h_t is split by the ONE thread that produces it and stored in the B-fragment order of m16n8k16,
+//     hF[k / 16][hi | lo][b0 | b1][(k % 8) / 2][item % 8][item / 8] (half2 = the two k of a register), so a lane fetches the four
+//     n-tiles of a fragment register with one 16-byte load (4 loads per k16 step, every byte used).
+// lstm_tc_kernel spent ~900 instructions per 4 k8 steps for 96 HMMA (ncu: 30 % of the stall samples on HMMA, 29 % fixed-latency waits
+// of the conversion chains); here a k16 step is 4 LDG.128 + 4 LDS.128 + 24 HMMA.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_h2(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
+}
+constexpr int LH2_PB = 4;   // k16 steps of B fragments requested together
+__global__ void __launch_bounds__(LTC_NW * 32, 1) lstm_h2_kernel(LstmParams p) {
+    extern __shared__ float smem[];
+    const int H = p.H;
+    uint4* wfrag = reinterpret_cast<uint4*>(smem);                 // [warp][k16 step][m tile][hi | lo][lane]
+    float* red = smem + (size_t)LTC_ROWS * H;                      // [8 warps][32 rows][33]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+    const int unit0 = blockIdx.x * LTC_U;
+    const unsigned ncta = gridDim.x;
+    const int ksteps = H / (16 * LTC_NW);        // k16 steps per warp
+    const int kb0 = warp * ksteps;               // first k16 block of this warp
+
+    // ---- W_hh slice -> fp16 hi / lo A fragments (once).  Fragment registers of m16n8k16: a0 = (row g, k 2c..2c+1), a1 = (g + 8, 2c..),
+    //      a2 = (g, 2c + 8..), a3 = (g + 8, 2c + 8..); tile row r = gate * 8 + unit  ->  W_hh row gate * H + unit0 + unit.
+    for (int s = 0; s < ksteps; ++s)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            __half2 hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = mt * 16 + g + (j & 1) * 8, gate = r / LTC_U, u = r - gate * LTC_U;
+                const int k = (kb0 + s) * 16 + 2 * c + (j >> 1) * 8;
+                const float2 w = __ldg(reinterpret_cast<const float2*>(p.whh + ((size_t)gate * H + unit0 + u) * H + k));
+                __half h0, l0, h1, l1;
+                split_h2(w.x, h0, l0);
+                split_h2(w.y, h1, l1);
+                hi[j] = __halves2half2(h0, h1);
+                lo[j] = __halves2half2(l0, l1);
+            }
+            uint4* dst = wfrag + ((size_t)((warp * ksteps + s) * 2 + mt) * 2) * 32 + lane;
+            dst[0] = make_uint4(*reinterpret_cast<uint32_t*>(&hi[0]), *reinterpret_cast<uint32_t*>(&hi[1]),
+                                *reinterpret_cast<uint32_t*>(&hi[2]), *reinterpret_cast<uint32_t*>(&hi[3]));
+            dst[32] = make_uint4(*reinterpret_cast<uint32_t*>(&lo[0]), *reinterpret_cast<uint32_t*>(&lo[1]),
+                                 *reinterpret_cast<uint32_t*>(&lo[2]), *reinterpret_cast<uint32_t*>(&lo[3]));
+        }
+    __syncthreads();
+
+    const int cu = (tid >> 5) & (LTC_U - 1), cb = tid & 31;   // threads 0..255 own one cell each: unit unit0 + cu, item cb
+    const bool cell_live = tid < LTC_U * 32 && cb < p.B;
+    const int kunit = unit0 + cu;
+    // hF half index of (k = kunit, item cb), hi term; the lo term sits 2 * 4 * 8 * 4 * 2 = 512 halves further
+    const size_t hf_cell = ((((size_t)(kunit >> 4) * 2 * 2 + ((kunit & 15) >> 3)) * 4 + ((kunit & 7) >> 1)) * 8 + (cb & 7)) * 8 +
+                           (size_t)(cb >> 3) * 2 + (kunit & 1);
+    const size_t hf_size = (size_t)H * LTC_B * 2;             // halves per buffer
+    const size_t gx_cell = ((size_t)cb * 4 * H + kunit) * p.T;
+    const size_t y_cell = ((size_t)cb * H + kunit) * p.T;
+    float cstate = 0.f;
+    __half* hbuf = reinterpret_cast<__half*>(p.hbuf);
+
+    float gxr[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cell_live) {
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) gxr[gt] = __ldg(p.gx + gx_cell + (size_t)gt * H * p.T);
+    }
+    for (int t = 0; t < p.T; ++t) {
+        const __half* hprev = hbuf + (size_t)(t & 1) * hf_size;
+        __half* hnext = hbuf + (size_t)((t + 1) & 1) * hf_size;
+        float gi = gxr[0], gf = gxr[1], gg = gxr[2], go = gxr[3];
+        if (cell_live && t + 1 < p.T) {
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt) gxr[gt] = __ldg(p.gx + gx_cell + (size_t)gt * H * p.T + t + 1);
+        }
+        if (t > 0) {
+            float acc0[2][4][4], acc1[2][4][4];   // hi.hi | hi.lo + lo.hi (scaled by 2^11)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc0[i][j][0] = acc0[i][j][1] = acc0[i][j][2] = acc0[i][j][3] = 0.f;
+                    acc1[i][j][0] = acc1[i][j][1] = acc1[i][j][2] = acc1[i][j][3] = 0.f;
+                }
+            const uint4* hf4 = reinterpret_cast<const uint4*>(hprev);   // [k16][hi|lo][b][c][g] of uint4 (4 n tiles)
+#pragma unroll 1
+            for (int s0 = 0; s0 < ksteps; s0 += LH2_PB) {
+                uint4 bf[LH2_PB][4];             // [step][hi b0, hi b1, lo b0, lo b1]
+#pragma unroll
+                for (int s = 0; s < LH2_PB; ++s) {
+                    if (s0 + s < ksteps) {       // warp-uniform
+                        const uint4* q = hf4 + (size_t)(kb0 + s0 + s) * 128 + c * 8 + g;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) bf[s][j] = __ldcg(q + j * 32);
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < LH2_PB; ++s) {
+                    if (s0 + s >= ksteps) break;
+                    const uint4* wf = wfrag + ((size_t)(warp * ksteps + s0 + s) * 2 * 2) * 32 + lane;
+                    const uint4 ah0 = wf[0], al0 = wf[32], ah1 = wf[64], al1 = wf[96];
+                    const uint32_t hb0[4] = {bf[s][0].x, bf[s][0].y, bf[s][0].z, bf[s][0].w};
+                    const uint32_t hb1[4] = {bf[s][1].x, bf[s][1].y, bf[s][1].z, bf[s][1].w};
+                    const uint32_t lb0[4] = {bf[s][2].x, bf[s][2].y, bf[s][2].z, bf[s][2].w};
+                    const uint32_t lb1[4] = {bf[s][3].x, bf[s][3].y, bf[s][3].z, bf[s][3].w};
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        mma_f16(acc0[0][nt], ah0, hb0[nt], hb1[nt]);
+                        mma_f16(acc0[1][nt], ah1, hb0[nt], hb1[nt]);
+                        mma_f16(acc1[0][nt], ah0, lb0[nt], lb1[nt]);
+                        mma_f16(acc1[1][nt], ah1, lb0[nt], lb1[nt]);
+                        mma_f16(acc1[0][nt], al0, hb0[nt], hb1[nt]);
+                        mma_f16(acc1[1][nt], al1, hb0[nt], hb1[nt]);
+                    }
+                }
+            }
+            float* rw = red + (size_t)warp * LTC_ROWS * 33;
+            constexpr float LO = 1.f / 2048.f;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    float* r0 = rw + (mt * 16 + g) * 33 + nt * 8 + 2 * c;
+                    r0[0] = fmaf(acc1[mt][nt][0], LO, acc0[mt][nt][0]);
+                    r0[1] = fmaf(acc1[mt][nt][1], LO, acc0[mt][nt][1]);
+                    r0[8 * 33] = fmaf(acc1[mt][nt][2], LO, acc0[mt][nt][2]);
+                    r0[8 * 33 + 1] = fmaf(acc1[mt][nt][3], LO, acc0[mt][nt][3]);
+                }
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < LTC_NW; ++w) {   // warp order: fixed summation order
+                const float* rr = red + (size_t)w * LTC_ROWS * 33 + cb;
+                gi += rr[(0 * LTC_U + cu) * 33];
+                gf += rr[(1 * LTC_U + cu) * 33];
+                gg += rr[(2 * LTC_U + cu) * 33];
+                go += rr[(3 * LTC_U + cu) * 33];
+            }
+        }
+        if (cell_live) {
+            cstate = sigmoidf_(gf) * cstate + sigmoidf_(gi) * tanhf(gg);
+            const float h = sigmoidf_(go) * tanhf(cstate);
+            __half hh, hl;
+            split_h2(h, hh, hl);
+            hnext[hf_cell] = hh;                 // plain stores: published by the release arrive below
+            hnext[hf_cell + 512] = hl;
+            p.y[y_cell + t] = p.skip ? h + p.skip[y_cell + t] : h;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            gridbar_arrive(p.bar);
+            gridbar_wait(p.bar, ncta * (unsigned)(t + 1));
+        }
+        __syncthreads();
+    }
+}
+
 extern "C" int64_t acb_lstm_state_bytes(int batch, int hidden) {
     const int64_t b = batch > LTC_B ? batch : LTC_B;   // the tensor-core kernel keeps h for 32 item slots
     return ((int64_t)2 * b * hidden + 64) * (int64_t)sizeof(float);
@@ -1831,7 +2000,11 @@ extern "C" int acb_lstm_recurrent(const float* gates_x, const float* w_hh, const
                 ACB_CHECK_CUDA(cudaMemsetAsync(state_ws, 0, (hfloats + 64) * sizeof(float), s));
                 LstmParams p{gates_x, w_hh, skip, y, state_ws, (unsigned*)(state_ws + hfloats), batch, hidden, t_len, LTC_U};
                 void* args[] = {&p};
-                ACB_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_kernel, dim3(ncta), dim3(LTC_NW * 32), args, smem_tc, s));
+                // hidden % 128 == 0: both operands pre-split into fp16 terms (lstm_h2_kernel); ACB_LSTM_TC=3 keeps the 3xTF32 kernel (A/B)
+                const bool h2 = hidden % (16 * LTC_NW) == 0 && !(e && e[0] == '3');
+                if (h2) ACB_CHECK_CUDA(cudaFuncSetAttribute(lstm_h2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+                ACB_CHECK_CUDA(cudaLaunchCooperativeKernel(h2 ? (void*)lstm_h2_kernel : (void*)lstm_tc_kernel, dim3(ncta), dim3(LTC_NW * 32),
+                                                           args, smem_tc, s));
                 return ACB_OK;
             }
         }

@@ -107,7 +107,8 @@ int acb_resblock(const float* x, const float* w1, const float* b1, const float* 
  *   y[b,:,t] = h_t (+ skip[b,:,t] if skip != NULL)       [B][H][T]
  * state_ws: acb_lstm_state_bytes(B, H) bytes of scratch = (2*max(B,32)*H + 64) floats (h double buffer, kept for 32 item slots in
  * MMA-fragment order by the tensor-core kernel, + grid-barrier counter), zeroed by the call.  hidden % 64 == 0 and B <= 32 run the
- * recurrent step on the tensor pipe (3xTF32, fp32 accumulate), other shapes on fp32 FMA.
+ * recurrent step on the tensor pipe (hidden % 128 == 0: both operands split into two fp16 terms, 22 mantissa bits; else 3xTF32;
+ * fp32 accumulate), other shapes on fp32 FMA.
  * NOT graph-capturable (cooperative launch). */
 int acb_lstm_recurrent(const float* gates_x, const float* w_hh, const float* skip, float* y, float* state_ws,
                        int batch, int hidden, int t_len, void* stream);
