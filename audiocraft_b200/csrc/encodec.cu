@@ -612,6 +612,295 @@ __global__ void __launch_bounds__(HD >= 128 ? 512 : 256, HD >= 128 ? 1 : 2) resb
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// resblock_kernel with both GEMM operands split into two fp16 terms instead of two tf32 terms (x = hi + lo 2^-11, hi = fp16(x),
+// lo = fp16((x - hi) 2^11): 22 mantissa bits, the class of the tf32 split; activations and folded weights of the codec sit well inside
+// fp16's range).  A 16-element reduction step is 3 mma.sync.m16n8k16 (hi.hi | hi.lo + lo.hi into a second accumulator that is scaled
+// by 2^-11 when it is folded in) instead of 6 m16n8k8, and the split happens ONCE per element while staging -- weights into half2
+// pairs of consecutive reduction rows [k pair][m], the ELU'd slab and the hidden tile into half2 pairs of consecutive channels
+// [channel pair][step] -- so the inner loops are LDS + HMMA only (the tf32 kernel: ~10 split instructions per B element and use).
+// Same tiling, chunking, epilogue and FLUSH rule (a tensor-core accumulation run covers 16 input channels x 3 taps, resp. 16 hidden
+// channels, then goes to fp32 registers) as resblock_kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_f16r(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// two values -> (half2 of the high terms, half2 of the scaled low terms); .x = first value (even reduction index)
+__device__ __forceinline__ void split2_h2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((v0 - hf.x) * 2048.f, (v1 - hf.y) * 2048.f);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int HD, bool FLUSH>
+__global__ void __launch_bounds__(HD >= 128 ? 512 : 256, HD >= 128 ? 1 : 2) resblock_h2_kernel(ResblockParams p) {
+    constexpr int NTHR = HD >= 128 ? 512 : 256, NWARP = NTHR / 32, WM1 = NWARP / 4, MT1 = HD / (16 * WM1), WN2 = NWARP / 2, NT2 = 16 / WN2;
+    constexpr int C = 2 * HD, WP1 = HD + 8, WP2 = 64 + 8;
+    constexpr int KP1 = 3 * RB_CH / 2;                 // k pairs of a W1 chunk (16 channels x 3 taps)
+    constexpr int WHALF = (KP1 * WP1) > ((HD / 2) * WP2) ? (KP1 * WP1) : ((HD / 2) * WP2);
+    constexpr int NPR = (C / 2) * RB_XSP / NTHR, SLB = 17;   // slab channel PAIRS per thread (17 / 34 / 34), 17 pairs = 34 loads at a time
+    constexpr int NW1 = KP1 * HD / NTHR;               // W1 chunk k pairs per thread (3 / 6 / 6)
+    constexpr int NW2 = (HD / 2) * 64 / NTHR;          // W2 chunk k pairs per thread (4 / 8 / 8)
+    constexpr float LO = 1.f / 2048.f;
+    static_assert(NPR % SLB == 0 && (C / 2) * RB_XSP % NTHR == 0 && KP1 * HD % NTHR == 0, "staging");
+    extern __shared__ uint32_t rsm2[];
+    uint32_t* xh = rsm2;                       // [C/2][RB_XSP] half2 (channel 2i, 2i+1) high terms; after GEMM 1: hidden tile [HD/2][RB_XSP]
+    uint32_t* xl = xh + (C / 2) * RB_XSP;      // ... low terms (x 2^11)
+    uint32_t* wh = xl + (C / 2) * RB_XSP;      // weight chunk [k pair][m], high terms
+    uint32_t* wl = wh + WHALF;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+    const int wm = warp % WM1, wn = warp / WM1;     // GEMM 1
+    const int wm2 = warp & 1, wn2 = warp >> 1;      // GEMM 2
+    const int t0 = blockIdx.x * RB_TB, b = blockIdx.y;
+    const float* __restrict__ xb = p.x + (size_t)b * C * p.T;
+    const float* __restrict__ w1g = p.w1;
+    const float* __restrict__ w2g = p.w2;
+    const int span = RB_TB + 2 * p.dil;
+
+    float w1r[NW1][2];
+    auto load_w1 = [&](int ci0) {   // chunk row (tap, cl): k pair (tap, cl / 2) = channels ci0 + 2 j, 2 j + 1 at one tap
+#pragma unroll
+        for (int i = 0; i < NW1; ++i) {
+            const int idx = tid + NTHR * i, kp = idx / HD, m = idx - kp * HD, tap = kp / (RB_CH / 2), j = kp - tap * (RB_CH / 2);
+            const float* src = w1g + ((size_t)tap * C + ci0 + 2 * j) * HD + m;
+            w1r[i][0] = __ldg(src);
+            w1r[i][1] = __ldg(src + HD);
+        }
+    };
+    load_w1(0);
+#pragma unroll 1
+    for (int i0 = 0; i0 < NPR; i0 += SLB) {
+        float v[SLB][2];
+#pragma unroll
+        for (int i = 0; i < SLB; ++i) {
+            const int idx = tid + NTHR * (i0 + i), cp = idx / RB_XSP, j = idx - cp * RB_XSP;
+            int gt = t0 - p.pad_left + j;
+            if (p.reflect) {
+                if (gt < 0) gt = -gt;
+                if (gt >= p.T) gt = 2 * (p.T - 1) - gt;
+            }
+            const bool ok = j < span && gt >= 0 && gt < p.T;
+            v[i][0] = ok ? __ldg(xb + (size_t)(2 * cp) * p.T + gt) : 0.f;
+            v[i][1] = ok ? __ldg(xb + (size_t)(2 * cp + 1) * p.T + gt) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < SLB; ++i) {
+            uint32_t hi, lo;
+            split2_h2(acb_elu(v[i][0]), acb_elu(v[i][1]), hi, lo);
+            xh[tid + NTHR * (i0 + i)] = hi;
+            xl[tid + NTHR * (i0 + i)] = lo;
+        }
+    }
+
+    float acc1[MT1][4][4];                     // FLUSH: fp32 totals; else: the hi.hi accumulators
+    float accx[FLUSH ? 1 : MT1][4][4];         // !FLUSH: the cross-term accumulators (x 2^11)
+#pragma unroll
+    for (int i = 0; i < MT1; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc1[i][j][0] = acc1[i][j][1] = acc1[i][j][2] = acc1[i][j][3] = 0.f;
+    if (!FLUSH) {
+#pragma unroll
+        for (int i = 0; i < MT1; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) accx[i][j][0] = accx[i][j][1] = accx[i][j][2] = accx[i][j][3] = 0.f;
+    }
+
+#pragma unroll 1
+    for (int ci0 = 0; ci0 < C; ci0 += RB_CH) {
+        __syncthreads();   // slab complete (first pass) / previous weight chunk consumed
+#pragma unroll
+        for (int i = 0; i < NW1; ++i) {
+            const int idx = tid + NTHR * i, kp = idx / HD, m = idx - kp * HD;
+            uint32_t hi, lo;
+            split2_h2(w1r[i][0], w1r[i][1], hi, lo);
+            wh[kp * WP1 + m] = hi;
+            wl[kp * WP1 + m] = lo;
+        }
+        __syncthreads();
+        if (ci0 + RB_CH < C) load_w1(ci0 + RB_CH);   // next chunk's weights fly during this chunk's MMAs
+        // FLUSH: a run (this chunk: 3 taps x 16 channels) accumulates in c0 (hi.hi) / c1 (cross terms x 2^11) for one m tile and TWO of
+        // the warp's four n tiles at a time (16 registers; with all four live the 64- / 128-hidden-channel variants spilled), then folds
+        // into the fp32 totals.  Not FLUSH: straight into acc1 / accx, all four n tiles per A fragment.
+        constexpr int NH = FLUSH ? 2 : 1, NTH = 4 / NH;
+#pragma unroll
+        for (int mt = 0; mt < MT1; ++mt) {
+            const int m = wm * (16 * MT1) + mt * 16 + g;
+#pragma unroll
+            for (int nh = 0; nh < NH; ++nh) {
+                float c0[NTH][4], c1[NTH][4];
+                if (FLUSH) {
+#pragma unroll
+                    for (int j = 0; j < NTH; ++j) {
+                        c0[j][0] = c0[j][1] = c0[j][2] = c0[j][3] = 0.f;
+                        c1[j][0] = c1[j][1] = c1[j][2] = c1[j][3] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int tap = 0; tap < 3; ++tap) {
+                    const int kr = tap * (RB_CH / 2);
+                    uint32_t ah[4], al[4];           // a0 = (m, k pair c), a1 = (m + 8, c), a2 = (m, c + 4), a3 = (m + 8, c + 4)
+                    ah[0] = wh[(kr + c) * WP1 + m];     ah[1] = wh[(kr + c) * WP1 + m + 8];
+                    ah[2] = wh[(kr + c + 4) * WP1 + m]; ah[3] = wh[(kr + c + 4) * WP1 + m + 8];
+                    al[0] = wl[(kr + c) * WP1 + m];     al[1] = wl[(kr + c) * WP1 + m + 8];
+                    al[2] = wl[(kr + c + 4) * WP1 + m]; al[3] = wl[(kr + c + 4) * WP1 + m + 8];
+                    const int xo = (ci0 / 2 + c) * RB_XSP + tap * p.dil + wn * 32 + g;   // b0 = (k pair c, step g), b1 = (k pair c + 4, g)
+#pragma unroll
+                    for (int j = 0; j < NTH; ++j) {
+                        const int nt = nh * NTH + j;
+                        const uint32_t bh0 = xh[xo + nt * 8], bh1 = xh[xo + 4 * RB_XSP + nt * 8];
+                        const uint32_t bl0 = xl[xo + nt * 8], bl1 = xl[xo + 4 * RB_XSP + nt * 8];
+                        float (&d0)[4] = FLUSH ? c0[j] : acc1[mt][nt];
+                        float (&d1)[4] = FLUSH ? c1[j] : accx[FLUSH ? 0 : mt][nt];
+                        mma_f16r(d0, ah, bh0, bh1);
+                        mma_f16r(d1, ah, bl0, bl1);
+                        mma_f16r(d1, al, bh0, bh1);
+                    }
+                }
+                if (FLUSH) {
+#pragma unroll
+                    for (int j = 0; j < NTH; ++j)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc1[mt][nh * NTH + j][e] += fmaf(c1[j][e], LO, c0[j][e]);
+                }
+            }
+        }
+    }
+    if (!FLUSH) {
+#pragma unroll
+        for (int i = 0; i < MT1; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc1[i][j][e] = fmaf(accx[i][j][e], LO, acc1[i][j][e]);
+    }
+    float w2r[NW2][2];
+    auto load_w2 = [&](int co0) {
+#pragma unroll
+        for (int i = 0; i < NW2; ++i) {
+            const int idx = tid + NTHR * i, kp = idx >> 6, m = idx & 63;
+            const float* src = w2g + (size_t)(2 * kp) * C + co0 + m;
+            w2r[i][0] = __ldg(src);
+            w2r[i][1] = __ldg(src + C);
+        }
+    };
+    load_w2(0);
+    __syncthreads();   // every warp is done with the slab and the last W1 chunk
+    // hidden tile -> shared memory (bias + ELU + split), over the slab, as half2 pairs of consecutive hidden channels: rows m (lane
+    // group g) and m + 1 (g + 1) sit 4 lanes apart; the even row's lane packs step 2c, the odd row's lane step 2c + 1.
+#pragma unroll
+    for (int mt = 0; mt < MT1; ++mt)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int m = wm * (16 * MT1) + mt * 16 + g + 8 * hrow;
+            const float bv = __ldg(p.b1 + m);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float v0 = acb_elu(acc1[mt][nt][2 * hrow] + bv), v1 = acb_elu(acc1[mt][nt][2 * hrow + 1] + bv);
+                const bool even = (g & 1) == 0;
+                const float recv = __shfl_xor_sync(0xffffffffu, even ? v1 : v0, 4);   // partner row's value at the step this lane packs
+                uint32_t hi, lo;
+                if (even) split2_h2(v0, recv, hi, lo);     // (row m, row m + 1) at step 2c
+                else split2_h2(recv, v1, hi, lo);          // (row m - 1, row m) at step 2c + 1
+                const int t = wn * 32 + nt * 8 + 2 * c + (even ? 0 : 1);
+                xh[(m >> 1) * RB_XSP + t] = hi;
+                xl[(m >> 1) * RB_XSP + t] = lo;
+            }
+        }
+
+    const bool pair_ok = (p.T & 1) == 0;   // row bases even -> the (t, t+1) pairs of the epilogue are 8-byte aligned
+#pragma unroll 1
+    for (int co0 = 0; co0 < C; co0 += 64) {
+        if (co0) __syncthreads();   // previous W2 chunk consumed
+#pragma unroll
+        for (int i = 0; i < NW2; ++i) {
+            const int idx = tid + NTHR * i, kp = idx >> 6, m = idx & 63;
+            uint32_t hi, lo;
+            split2_h2(w2r[i][0], w2r[i][1], hi, lo);
+            wh[kp * WP2 + m] = hi;
+            wl[kp * WP2 + m] = lo;
+        }
+        __syncthreads();   // W2 chunk (and, first pass, the hidden tile) visible
+        if (co0 + 64 < C) load_w2(co0 + 64);
+        float acc2[2][NT2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < NT2; ++j) acc2[i][j][0] = acc2[i][j][1] = acc2[i][j][2] = acc2[i][j][3] = 0.f;
+#pragma unroll 1
+        for (int kb = 0; kb < HD / 16; ++kb) {      // one k16 step = 16 hidden channels = one tensor-core accumulation run
+            const int ho = (kb * 8 + c) * RB_XSP + wn2 * (8 * NT2) + g;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {        // one m tile at a time: 2 x NT2 x 4 run accumulators live instead of 4 x
+                float c0[NT2][4], c1[NT2][4];
+#pragma unroll
+                for (int j = 0; j < NT2; ++j) {
+                    c0[j][0] = c0[j][1] = c0[j][2] = c0[j][3] = 0.f;
+                    c1[j][0] = c1[j][1] = c1[j][2] = c1[j][3] = 0.f;
+                }
+                const int m = wm2 * 32 + mt * 16 + g, kr = kb * 8;
+                uint32_t ah[4], al[4];
+                ah[0] = wh[(kr + c) * WP2 + m];     ah[1] = wh[(kr + c) * WP2 + m + 8];
+                ah[2] = wh[(kr + c + 4) * WP2 + m]; ah[3] = wh[(kr + c + 4) * WP2 + m + 8];
+                al[0] = wl[(kr + c) * WP2 + m];     al[1] = wl[(kr + c) * WP2 + m + 8];
+                al[2] = wl[(kr + c + 4) * WP2 + m]; al[3] = wl[(kr + c + 4) * WP2 + m + 8];
+#pragma unroll
+                for (int nt = 0; nt < NT2; ++nt) {
+                    const uint32_t bh0 = xh[ho + nt * 8], bh1 = xh[ho + 4 * RB_XSP + nt * 8];
+                    const uint32_t bl0 = xl[ho + nt * 8], bl1 = xl[ho + 4 * RB_XSP + nt * 8];
+                    mma_f16r(c0[nt], ah, bh0, bh1);
+                    mma_f16r(c1[nt], ah, bl0, bl1);
+                    mma_f16r(c1[nt], al, bh0, bh1);
+                }
+#pragma unroll
+                for (int j = 0; j < NT2; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc2[mt][j][e] += fmaf(c1[j][e], LO, c0[j][e]);
+            }
+        }
+        // the skip connection under this warp's output tile
+        float2 xsk[2][2][NT2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int co = co0 + wm2 * 32 + mt * 16 + g + 8 * hrow;
+                const float* __restrict__ xr = xb + (size_t)co * p.T;
+#pragma unroll
+                for (int nt = 0; nt < NT2; ++nt) {
+                    const int t = t0 + wn2 * (8 * NT2) + nt * 8 + 2 * c;
+                    if (pair_ok && t + 1 < p.T) xsk[mt][hrow][nt] = __ldg(reinterpret_cast<const float2*>(xr + t));
+                    else xsk[mt][hrow][nt] = make_float2(t < p.T ? __ldg(xr + t) : 0.f, t + 1 < p.T ? __ldg(xr + t + 1) : 0.f);
+                }
+            }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int co = co0 + wm2 * 32 + mt * 16 + g + 8 * hrow;
+                const float bv = __ldg(p.b2 + co);
+                float* yr = p.y + ((size_t)b * C + co) * p.T;
+#pragma unroll
+                for (int nt = 0; nt < NT2; ++nt) {
+                    const int t = t0 + wn2 * (8 * NT2) + nt * 8 + 2 * c;
+                    const float v0 = acc2[mt][nt][2 * hrow] + bv + xsk[mt][hrow][nt].x;
+                    const float v1 = acc2[mt][nt][2 * hrow + 1] + bv + xsk[mt][hrow][nt].y;
+                    if (pair_ok && t + 1 < p.T) {
+                        *reinterpret_cast<float2*>(yr + t) = make_float2(v0, v1);
+                    } else {
+                        if (t < p.T) yr[t] = v0;
+                        if (t + 1 < p.T) yr[t + 1] = v1;
+                    }
+                }
+            }
+    }
+}
+
 template <int HD, bool FLUSH>
 static int launch_resblock_one(const ResblockParams& p, int batch, cudaStream_t s) {
     constexpr int C = 2 * HD, WP1 = HD + 8, WP2 = 72;
@@ -620,6 +909,18 @@ static int launch_resblock_one(const ResblockParams& p, int batch, cudaStream_t 
     ACB_CHECK_CUDA(cudaFuncSetAttribute(resblock_kernel<HD, FLUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(acb_ceil_div(p.T, RB_TB), batch);
     resblock_kernel<HD, FLUSH><<<grid, HD >= 128 ? 512 : 256, smem, s>>>(p);
+    ACB_LAUNCH_CHECK();
+    return ACB_OK;
+}
+
+template <int HD, bool FLUSH>
+static int launch_resblock_h2(const ResblockParams& p, int batch, cudaStream_t s) {
+    constexpr int C = 2 * HD, WP1 = HD + 8, WP2 = 72, KP1 = 3 * RB_CH / 2;
+    constexpr int WHALF = (KP1 * WP1) > ((HD / 2) * WP2) ? (KP1 * WP1) : ((HD / 2) * WP2);
+    const size_t smem = ((size_t)C * RB_XSP + 2 * (size_t)WHALF) * sizeof(uint32_t);
+    ACB_CHECK_CUDA(cudaFuncSetAttribute(resblock_h2_kernel<HD, FLUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(acb_ceil_div(p.T, RB_TB), batch);
+    resblock_h2_kernel<HD, FLUSH><<<grid, HD >= 128 ? 512 : 256, smem, s>>>(p);
     ACB_LAUNCH_CHECK();
     return ACB_OK;
 }
@@ -636,6 +937,16 @@ extern "C" int acb_resblock(const float* x, const float* w1, const float* b1, co
     ACB_REQUIRE(!reflect || t_len > 2 * dilation, "acb_resblock: reflect padding needs t_len > %d", 2 * dilation);
     ResblockParams p{x, w1, b1, w2, b2, y, t_len, dilation, pad_left, reflect};
     cudaStream_t s = (cudaStream_t)stream;
+    {   // default: operands split into fp16 terms (resblock_h2_kernel); ACB_RESBLOCK_TF32=1 keeps the 3xTF32 kernel (A/B)
+        const char* e = getenv("ACB_RESBLOCK_TF32");
+        if (!(e && e[0] == '1')) {
+            switch (channels) {
+                case 64: return exact ? launch_resblock_h2<32, true>(p, batch, s) : launch_resblock_h2<32, false>(p, batch, s);
+                case 128: return exact ? launch_resblock_h2<64, true>(p, batch, s) : launch_resblock_h2<64, false>(p, batch, s);
+                default: return exact ? launch_resblock_h2<128, true>(p, batch, s) : launch_resblock_h2<128, false>(p, batch, s);
+            }
+        }
+    }
     switch (channels) {
         case 64: return exact ? launch_resblock_one<32, true>(p, batch, s) : launch_resblock_one<32, false>(p, batch, s);
         case 128: return exact ? launch_resblock_one<64, true>(p, batch, s) : launch_resblock_one<64, false>(p, batch, s);

@@ -88,8 +88,9 @@ int acb_conv1d_t6(const float* x, const float* w6, const float* bias, const floa
 int acb_conv1d_t6_tile(int c_out);   /* output-channel tile (128, 64, or 0 = shape not supported) */
 /* SEANetResnetBlock.forward with the identity skip (audiocraft/modules/seanet.py:44-69, true_skip=True; one residual layer of
  * kernel sizes [k, 1]) as one kernel:  y = x + conv1x1(elu(conv_k(elu(x)))).  w1 is the first conv's folded weight packed
- * [k][C][C/2] (tap-major), w2 the second conv's packed [C/2][C]; pad_left / reflect as acb_conv1d (stride 1).  3xTF32 on the
- * tensor pipe; exact != 0 bounds every tensor-core accumulation run to 24 (resp. 16) reduction rows with fp32 adds in between
+ * [k][C][C/2] (tap-major), w2 the second conv's packed [C/2][C]; pad_left / reflect as acb_conv1d (stride 1).  Tensor pipe with
+ * every fp32 operand split into two fp16 terms (22 mantissa bits; |values| must stay below fp16's 65504), three MMAs per product;
+ * exact != 0 bounds every tensor-core accumulation run to 48 (resp. 16) reduction rows with fp32 adds in between
  * (the encoder setting: RVQ indices equal the fp32 reference's).  x and y must not alias. */
 int acb_resblock_supported(int channels, int kernel, int dilation);
 int acb_resblock(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int batch,

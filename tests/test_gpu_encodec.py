@@ -87,12 +87,15 @@ def test_experimental_conv1d_t6_matches_oracle(cin, cout, k, s, d, causal, L):
 
 @pytest.mark.parametrize('C,d,causal,L,B', [(64, 1, False, 1000, 2), (64, 1, False, 128, 1), (128, 1, False, 333, 3), (256, 1, False, 257, 2),
                                            (64, 2, False, 517, 2), (128, 1, True, 130, 2), (64, 1, False, 3, 1), (256, 3, True, 1025, 1)])
-def test_resblock_matches_oracle(C, d, causal, L, B):
+@pytest.mark.parametrize('split', ['fp16x2', 'tf32x3'])
+def test_resblock_matches_oracle(monkeypatch, split, C, d, causal, L, B):
     """SEANetResnetBlock with the identity skip as one kernel (acb_resblock; seanet.py:44-69): y = x + conv1x1(elu(conv3(elu(x)))).
     exact = 1 (the encoder setting, tensor-core runs cut every 24 / 16 reduction rows) to 2e-5, exact = 0 (3xTF32 straight) to 1e-4 --
     the tolerances of the flushed / un-flushed single-layer kernels."""
     from audiocraft_b200.encodec import conv_geometry
     lib, L_ = _lib()
+    if split == 'tf32x3':      # the round-2 first version of the kernel (operands split into tf32 terms); default: fp16 terms
+        monkeypatch.setenv('ACB_RESBLOCK_TF32', '1')
     assert L_.acb_resblock_supported(C, 3, d) == 1 and L_.acb_resblock_supported(512, 3, 1) == 0
     g = torch.Generator().manual_seed(C * 100 + d * 10 + L)
     x = torch.randn(B, C, L, generator=g)
@@ -112,7 +115,7 @@ def test_resblock_matches_oracle(C, d, causal, L, B):
         lib.check(L_.acb_resblock(lib.ptr(xd), lib.ptr(w1d), lib.ptr(b1d), lib.ptr(w2d), lib.ptr(b2d), lib.ptr(y), B, C, L, 3, d,
                                   left, 1, exact, lib.stream()))
         torch.cuda.synchronize()
-        print(f'resblock C={C} dil={d} L={L} exact={exact}: max err {(y.cpu() - ref).abs().max():.2e}')
+        print(f'resblock[{split}] C={C} dil={d} L={L} exact={exact}: max err {(y.cpu() - ref).abs().max():.2e}')
         torch.testing.assert_close(y.cpu(), ref, rtol=tol, atol=tol)
 
 
