@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(HD >= 128 ? 512 : 256, HD >= 128 ? 1 : 2) resb
     // of MT1 m16 tiles and 4 warp columns of 32 steps; GEMM 2 (64 output channels per pass) uses 2 warp rows x WN2 warp columns.
     constexpr int NTHR = HD >= 128 ? 512 : 256, NWARP = NTHR / 32, WM1 = NWARP / 4, MT1 = HD / (16 * WM1), WN2 = NWARP / 2, NT2 = 16 / WN2;
     constexpr int C = 2 * HD, WP1 = HD + 8, WP2 = 64 + 8;
-    constexpr bool EARLY_SKIP = !FLUSH || HD == 32;
-    constexpr bool PF_W2 = !(FLUSH && HD == 64);      // next W2 chunk prefetched into registers during the MMAs (registers permitting)   // skip-connection loads before the MMAs of a pass (registers permitting) or after
+    constexpr bool EARLY_SKIP = !FLUSH || HD == 32;   // skip-connection loads before the MMAs of a pass (registers permitting) or after
+    constexpr bool PF_W2 = !(FLUSH && HD == 64);      // next W2 chunk prefetched into registers during the MMAs (registers permitting)
     constexpr int WHALF = (3 * RB_CH * WP1) > (HD * WP2) ? (3 * RB_CH * WP1) : (HD * WP2);
     constexpr int NSL = C * RB_XSP / NTHR, SLB = 34;   // slab elements per thread (34 / 68 / 68), requested 34 at a time (ncu: 21 % of the
                                                        // stall samples were the first use of a 17-element batch, twice per tile at 64 channels)
