@@ -27,6 +27,41 @@ def test_library_exports_every_declared_symbol():
     assert L.acb_lstm_state_bytes(40, 8) == (2 * 40 * 8 + 64) * 4
 
 
+def test_fused_residual_block_routing():
+    """Which SEANet residual blocks go to acb_resblock (host rule in EncodecModel._fused_block, no GPU needed): the 32 kHz model's
+    identity-skip blocks at 64 / 128 / 256 channels yes; 32 / 512 channels, conv-shortcut blocks and the all-FMA precision no."""
+    from types import SimpleNamespace
+    from audiocraft_b200 import _lib
+    from audiocraft_b200.encodec import EncodecModel, encodec_layers
+    L = _lib.lib()
+    assert [L.acb_resblock_supported(c, 3, 1) for c in (32, 64, 128, 256, 512)] == [0, 1, 1, 1, 0]
+    assert L.acb_resblock_supported(64, 3, 4) == 1 and L.acb_resblock_supported(64, 3, 5) == 0 and L.acb_resblock_supported(64, 5, 1) == 0
+    stub = SimpleNamespace(_fuse_blocks=True, _lib=L)
+
+    def fused(cfg_name, prec):
+        plan = encodec_layers(synth.ENCODEC_CONFIGS[cfg_name])
+        out = []
+        for part in ('encoder', 'decoder'):
+            layers, have_shortcut = plan[part], False
+            for i, lay in enumerate(layers):
+                if lay['kind'] == 'conv' and lay['res'] == 'shortcut':
+                    have_shortcut = True
+                if not have_shortcut and EncodecModel._fused_block(stub, layers, i, prec, 4000):
+                    out.append(layers[i + 1]['cout'])
+                if lay['kind'] == 'conv' and lay['res'] == 'out':
+                    have_shortcut = False
+        return out
+
+    assert fused('encodec_32k', _lib.CONV_T6_AUTO) == [64, 128, 256, 256, 128, 64]      # encoder then decoder; the 512-channel blocks stay two kernels
+    assert fused('encodec_32k', _lib.CONV_TF32X3) == [64, 128, 256, 256, 128, 64]
+    assert fused('encodec_32k', _lib.CONV_FP32) == []                                     # 'fp32' = every convolution on FMA
+    assert fused('encodec_24k', _lib.CONV_T6_AUTO) == [64, 128, 256, 256, 128, 64]       # 32 -> 512 channels: the 32- and 512-channel blocks stay two kernels
+    plan = encodec_layers(dict(synth.ENCODEC_CONFIGS['encodec_32k'], true_skip=False))      # conv shortcut (the HF EnCodec layout): never fused
+    assert any(lay.get('res') == 'shortcut' for lay in plan['encoder'])
+    stub._fuse_blocks = False
+    assert fused('encodec_32k', _lib.CONV_T6_AUTO) == []
+
+
 def test_sass_is_sm100a():
     import subprocess
     from audiocraft_b200 import _lib
