@@ -2142,7 +2142,7 @@ __device__ __forceinline__ void split_h2(float v, __half& hi, __half& lo) {
     hi = __float2half_rn(v);
     lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
 }
-constexpr int LH2_PB = 4;   // k16 steps of B fragments requested together
+constexpr int LH2_PB = 4;   // k16 steps of B fragments requested together (all 8 at once, 254 registers: 12.4 vs 11.5 ms per LSTM block)
 __global__ void __launch_bounds__(LTC_NW * 32, 1) lstm_h2_kernel(LstmParams p) {
     extern __shared__ float smem[];
     const int H = p.H;
