@@ -145,6 +145,9 @@ class EncodecModel(CompressionModel):
                          run `acb_conv1d_t6` (tcgen05, 3xTF32 operand split, the TMEM accumulator flushed into fp32 registers
                          every 8 input channels), the rest fp32 FMA.  Latents within 3.0e-6 of the fp32 reference on the 24 /
                          32 kHz architectures (all-FMA: 3.6e-6), RVQ indices exact (profiles/r2_t6_first_hardware_contact_*.log);
+                         Residual blocks with the identity skip at 64 / 128 / 256 channels run as ONE kernel (`acb_resblock`, both
+                         operands split into two fp16 terms = 22 mantissa bits, tensor-core accumulation runs cut every 48 / 16
+                         reduction rows) in every precision except 'fp32'; the LSTM's recurrent step uses the same split;
           'tf32x3_flush' the same kernel on every layer it supports (slower on 1x1 convolutions; kept for tests);
           'tf32x3'       (decoder default, NOT fp32-exact) tcgen05 3xTF32 without flushes: the decoder's output is a waveform
                          checked to a tolerance of 1e-4; as an encoder mode its latents move by 1.5e-4."""
